@@ -1,0 +1,572 @@
+// C-ABI implementation (include/wavernn_b200.h): handle management, weight repack, launches.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "../../include/wavernn_b200.h"
+#include "wavernn_kernel.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace wrnn;
+
+static thread_local std::string g_err;
+static long long g_epilogue_launches = 0;
+
+static int32_t fail(int32_t code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail(WRNN_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct wrnn_handle {
+    wrnn_config cfg;
+    int device = 0, sm_count = 0;
+    int rows5 = 4, nprod5 = 128, cpad = 512, n_u = 1;
+    int smem_bytes = 0;
+    bool loaded = false;
+    float *wimg = nullptr, *xb = nullptr;
+    unsigned *flags = nullptr;
+    int *status = nullptr;
+    long long *fold_dev = nullptr;   // [2][fold_cap]
+    int fold_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0, epilogue_launches = 0;
+    int last_status = 0;
+    float last_ms = 0.f;
+    double *fade_dev = nullptr;      // cached epilogue tables [fade_in | fade_out | tail]
+    int fade_overlap = -1, fade_tail = -1;
+};
+
+extern "C" int32_t wrnn_abi_version(void) { return WRNN_ABI_VERSION; }
+extern "C" const char *wrnn_last_error(void) { return g_err.c_str(); }
+
+// fold_with_overlap index arithmetic -- fatchord_version.py:298-309
+extern "C" int32_t wrnn_fold_index(int64_t total_len, int64_t target, int64_t overlap,
+                                   int64_t *num_folds, int64_t *padded_len)
+{
+    if (!num_folds || !padded_len) return fail(WRNN_ERR_INVALID, "null output pointer");
+    if (target < 0 || overlap < 0 || target + overlap <= 0 || total_len < 0)
+        return fail(WRNN_ERR_INVALID, "fold_index: need target >= 0, overlap >= 0, target+overlap > 0, total_len >= 0");
+    const int64_t hop = target + overlap;
+    int64_t num = total_len - overlap, n = num / hop;
+    if (num % hop != 0 && num < 0) --n;                        // python floor division
+    const int64_t remaining = total_len - (n * hop + overlap);
+    int64_t plen = total_len;
+    if (remaining != 0) {
+        n += 1;
+        plen = total_len + (target + 2 * overlap - remaining);
+    }
+    *num_folds = n;
+    *padded_len = plen;
+    return WRNN_OK;
+}
+
+static int32_t derive_layout(const wrnn_config &c, int &rows5, int &nprod5, int &n_u)
+{
+    if (c.rnn_dims != HID || c.fc_dims != HID)
+        return fail(WRNN_ERR_INVALID, "this build keeps rnn_dims == fc_dims == %d resident (got %d / %d)", HID, c.rnn_dims, c.fc_dims);
+    if (c.feat_dims != 80 || c.aux_dims != 32)
+        return fail(WRNN_ERR_INVALID, "conditioning layout is fixed to feat_dims 80 + 4 x aux_dims 32 (got %d, %d)", c.feat_dims, c.aux_dims);
+    if (c.precision != WRNN_PREC_FP32)
+        return fail(WRNN_ERR_INVALID, "precision %d not available in this build (fp32 only)", c.precision);
+    if (c.mode == WRNN_MODE_RAW) {
+        const int C = c.n_classes;
+        if (C != 64 && C != 128 && C != 256 && C != 512 && C != 1024)
+            return fail(WRNN_ERR_INVALID, "RAW n_classes must be 2**bits with bits in 6..10 (got %d)", C);
+        rows5 = C > 512 ? C / NCTA : 4;
+        nprod5 = C / rows5;
+        n_u = 1;
+    } else if (c.mode == WRNN_MODE_MOL) {
+        if (c.n_classes != 30) return fail(WRNN_ERR_INVALID, "MOL n_classes must be 30 (got %d)", c.n_classes);
+        rows5 = 4;
+        nprod5 = 8;
+        n_u = 11;
+    } else
+        return fail(WRNN_ERR_INVALID, "unknown mode %d", c.mode);
+    return WRNN_OK;
+}
+
+extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_handle **out)
+{
+    if (!cfg || !out) return fail(WRNN_ERR_INVALID, "null argument");
+    int rows5, nprod5, n_u;
+    int32_t rc = derive_layout(*cfg, rows5, nprod5, n_u);
+    if (rc) return rc;
+    int ndev = 0;
+    CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(WRNN_ERR_CUDA, "device %d not present (%d CUDA devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(WRNN_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    if (prop.multiProcessorCount < NCTA) return fail(WRNN_ERR_CUDA, "need >= %d SMs, device has %d", NCTA, prop.multiProcessorCount);
+    int coop = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) return fail(WRNN_ERR_CUDA, "device does not support cooperative launch");
+
+    wrnn_handle *h = new wrnn_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    h->rows5 = rows5;
+    h->nprod5 = nprod5;
+    h->n_u = n_u;
+    h->cpad = rows5 * nprod5;
+    h->smem_bytes = smem_map(rows5).total * (int)sizeof(float);
+    if ((size_t)h->smem_bytes > prop.sharedMemPerBlockOptin) {
+        const int need = h->smem_bytes;
+        delete h;
+        return fail(WRNN_ERR_CUDA, "kernel needs %d B shared memory, device allows %zu", need, prop.sharedMemPerBlockOptin);
+    }
+    cudaError_t e;
+#define H_TRY(expr)                                                                  \
+    if ((e = (expr)) != cudaSuccess) {                                               \
+        wrnn_destroy(h);                                                             \
+        return fail(WRNN_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e));          \
+    }
+    H_TRY(cudaFuncSetAttribute(wavernn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    H_TRY(cudaFuncSetAttribute(wavernn_exchange_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    int occ = 0;
+    H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wavernn_persistent_kernel, NTHREADS, h->smem_bytes));
+    if (occ < 1) {
+        wrnn_destroy(h);
+        return fail(WRNN_ERR_CUDA, "persistent kernel does not fit on an SM");
+    }
+    H_TRY(cudaMalloc(&h->wimg, (size_t)NCTA * w_total(rows5) * sizeof(float)));
+    H_TRY(cudaMalloc(&h->xb, (size_t)MAXG * xb_group(h->cpad) * sizeof(float)));
+    H_TRY(cudaMemset(h->xb, 0, (size_t)MAXG * xb_group(h->cpad) * sizeof(float)));
+    H_TRY(cudaMalloc(&h->flags, (size_t)MAXG * NEXCH * NCTA * sizeof(unsigned)));
+    H_TRY(cudaMalloc(&h->status, 4 * sizeof(int)));
+    H_TRY(cudaEventCreate(&h->ev0));
+    H_TRY(cudaEventCreate(&h->ev1));
+#undef H_TRY
+    *out = h;
+    return WRNN_OK;
+}
+
+extern "C" void wrnn_destroy(wrnn_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->wimg);
+    cudaFree(h->xb);
+    cudaFree(h->flags);
+    cudaFree(h->status);
+    cudaFree(h->fold_dev);
+    cudaFree(h->fade_dev);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    delete h;
+}
+
+// ---- weight repack ---------------------------------------------------------------------------
+// out[M][N] = A[M][K(lda)] (fp32) * Bm[K][N] (fp64), accumulated in fp64
+static void gemm_f64(const float *A, int lda, int M, int K, const std::vector<double> &Bm, int N, std::vector<double> &out)
+{
+    out.assign((size_t)M * N, 0.0);
+    for (int i = 0; i < M; ++i) {
+        double *o = &out[(size_t)i * N];
+        const float *a = A + (size_t)i * lda;
+        for (int k = 0; k < K; ++k) {
+            const double av = a[k];
+            const double *b = &Bm[(size_t)k * N];
+            for (int j = 0; j < N; ++j) o[j] += av * b[j];
+        }
+    }
+}
+
+// write one item image: rows r0..r0+3 (callback per row), columns kbase..kbase+127
+template <class F>
+static void put_item(float *dst, int kbase, F rowval)
+{
+    for (int r = 0; r < 4; ++r)
+        for (int l = 0; l < 32; ++l)
+            for (int i = 0; i < 4; ++i) dst[(r * 32 + l) * 4 + i] = (float)rowval(r, kbase + l + 32 * i);
+}
+
+// Build the per-CTA shared-memory images (host, fp64 folding).  img: [NCTA][w_total(rows5)].
+static void pack_images(int C, int rows5, const wrnn_weights *w, std::vector<float> &img)
+{
+    const int R = HID, F = 80, A = 32, KI = 1 + F + A, KC = F + A;   // I: [512, 113]
+
+    // folded products in fp64:  Wc = I.weight[:, 1:], w0 = I.weight[:, 0]
+    std::vector<double> Wc((size_t)R * KC), w0(R), bI(R);
+    for (int j = 0; j < R; ++j) {
+        w0[j] = w->I_w[(size_t)j * KI];
+        bI[j] = w->I_b[j];
+        for (int k = 0; k < KC; ++k) Wc[(size_t)j * KC + k] = w->I_w[(size_t)j * KI + 1 + k];
+    }
+    std::vector<double> G1, G2, G3, u1, u2, u3, c1, c2, c3;
+    gemm_f64(w->r1_wih, R, 3 * R, R, Wc, KC, G1);
+    gemm_f64(w->r2_wih, R + A, 3 * R, R, Wc, KC, G2);
+    gemm_f64(w->fc1_w, R + A, R, R, Wc, KC, G3);
+    gemm_f64(w->r1_wih, R, 3 * R, R, w0, 1, u1);
+    gemm_f64(w->r2_wih, R + A, 3 * R, R, w0, 1, u2);
+    gemm_f64(w->fc1_w, R + A, R, R, w0, 1, u3);
+    gemm_f64(w->r1_wih, R, 3 * R, R, bI, 1, c1);
+    gemm_f64(w->r2_wih, R + A, 3 * R, R, bI, 1, c2);
+    gemm_f64(w->fc1_w, R + A, R, R, bI, 1, c3);
+
+    const size_t per = (size_t)w_total(rows5);
+    img.assign((size_t)NCTA * per, 0.f);
+    for (int c = 0; c < NCTA; ++c) {
+        float *base = &img[(size_t)c * per];
+        const int j0 = UNITS * c;
+        // M2: rg 0..2 = Wih2[:, :512] gate rows, rg 3..5 = Whh1 gate rows
+        for (int rg = 0; rg < 6; ++rg)
+            for (int kc = 0; kc < 4; ++kc)
+                put_item(base + W_M2 + (rg * 4 + kc) * ITEM, kc * 128, [&](int r, int k) -> double {
+                    const int row = j0 + r + R * (rg % 3);
+                    return rg < 3 ? w->r2_wih[(size_t)row * (R + A) + k] : w->r1_whh[(size_t)row * R + k];
+                });
+        // M3: rg 0 = fc1[:, :512] rows, rg 1..3 = Whh2 gate rows
+        for (int rg = 0; rg < 4; ++rg)
+            for (int kc = 0; kc < 4; ++kc)
+                put_item(base + W_M3 + (rg * 4 + kc) * ITEM, kc * 128, [&](int r, int k) -> double {
+                    if (rg == 0) return w->fc1_w[(size_t)(j0 + r) * (R + A) + k];
+                    return w->r2_whh[(size_t)(j0 + r + R * (rg - 1)) * R + k];
+                });
+        for (int kc = 0; kc < 4; ++kc)
+            put_item(base + W_M4 + kc * ITEM, kc * 128, [&](int r, int k) -> double { return w->fc2_w[(size_t)(j0 + r) * (R + A) + k]; });
+        for (int rg = 0; rg < rows5 / 4; ++rg)
+            for (int kc = 0; kc < 4; ++kc)
+                put_item(base + W_M5 + (rg * 4 + kc) * ITEM, kc * 128, [&](int r, int k) -> double {
+                    const int cls = rows5 * c + rg * 4 + r;
+                    return cls < C ? w->fc3_w[(size_t)cls * R + k] : 0.0;
+                });
+        // conditioning items; cond k: [0,80) mel | [80,112) a1 | [112,144) a2 | [144,176) a3 | [176,208) a4
+        float *mc = base + w_mc(rows5);
+        for (int rg = 0; rg < 3; ++rg)                                        // P1 (chunk A)
+            put_item(mc + rg * ITEM, 0, [&](int r, int k) -> double { return k < KC ? G1[(size_t)(j0 + r + R * rg) * KC + k] : 0.0; });
+        for (int rg = 0; rg < 3; ++rg)                                        // P2 (chunks A, B)
+            for (int ch = 0; ch < 2; ++ch)
+                put_item(mc + (3 + rg * 2 + ch) * ITEM, ch * 128, [&](int r, int k) -> double {
+                    const int row = j0 + r + R * rg;
+                    if (k < KC) return G2[(size_t)row * KC + k];
+                    if (k < KC + A) return w->r2_wih[(size_t)row * (R + A) + R + (k - KC)];
+                    return 0.0;
+                });
+        for (int ch = 0; ch < 2; ++ch)                                        // P3 (chunks A, B)
+            put_item(mc + (9 + ch) * ITEM, ch * 128, [&](int r, int k) -> double {
+                const int row = j0 + r;
+                if (k < KC) return G3[(size_t)row * KC + k];
+                if (k >= KC + A && k < KC + 2 * A) return w->fc1_w[(size_t)row * (R + A) + R + (k - KC - A)];
+                return 0.0;
+            });
+        put_item(mc + 11 * ITEM, 128, [&](int r, int k) -> double {           // P4 (chunk B)
+            const int row = j0 + r;
+            if (k >= KC + 2 * A && k < KC + 3 * A) return w->fc2_w[(size_t)row * (R + A) + R + (k - KC - 2 * A)];
+            return 0.0;
+        });
+        float *sv = base + w_small(rows5);
+        for (int q = 0; q < 3; ++q)
+            for (int u = 0; u < UNITS; ++u) {
+                const int row = j0 + u + R * q;
+                sv[SV_U1 + q * 4 + u] = (float)u1[row];
+                sv[SV_B1 + q * 4 + u] = (float)(c1[row] + (double)w->r1_bih[row]);
+                sv[SV_BHH1 + q * 4 + u] = w->r1_bhh[row];
+                sv[SV_U2 + q * 4 + u] = (float)u2[row];
+                sv[SV_B2 + q * 4 + u] = (float)(c2[row] + (double)w->r2_bih[row]);
+                sv[SV_BHH2 + q * 4 + u] = w->r2_bhh[row];
+            }
+        for (int u = 0; u < UNITS; ++u) {
+            sv[SV_U3 + u] = (float)u3[j0 + u];
+            sv[SV_B3 + u] = (float)(c3[j0 + u] + (double)w->fc1_b[j0 + u]);
+            sv[SV_B4 + u] = w->fc2_b[j0 + u];
+        }
+        for (int r = 0; r < rows5; ++r) {
+            const int cls = rows5 * c + r;
+            sv[SV_B5 + r] = cls < C ? w->fc3_b[cls] : 0.f;
+        }
+    }
+}
+
+extern "C" int64_t wrnn_packed_floats(const wrnn_config *cfg)
+{
+    int rows5, nprod5, n_u;
+    if (!cfg || derive_layout(*cfg, rows5, nprod5, n_u)) return -1;
+    return (int64_t)NCTA * w_total(rows5);
+}
+
+extern "C" int32_t wrnn_pack_weights_host(const wrnn_config *cfg, const wrnn_weights *w, float *out, int64_t out_floats)
+{
+    if (!cfg || !w || !out) return fail(WRNN_ERR_INVALID, "null argument");
+    int rows5, nprod5, n_u;
+    int32_t rc = derive_layout(*cfg, rows5, nprod5, n_u);
+    if (rc) return rc;
+    if (out_floats != (int64_t)NCTA * w_total(rows5)) return fail(WRNN_ERR_INVALID, "out_floats must be %lld", (long long)NCTA * w_total(rows5));
+    std::vector<float> img;
+    pack_images(cfg->n_classes, rows5, w, img);
+    memcpy(out, img.data(), img.size() * sizeof(float));
+    return WRNN_OK;
+}
+
+extern "C" int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w)
+{
+    if (!h || !w) return fail(WRNN_ERR_INVALID, "null argument");
+    const float *const *pp = reinterpret_cast<const float *const *>(w);
+    for (int i = 0; i < 16; ++i)
+        if (!pp[i]) return fail(WRNN_ERR_INVALID, "weight pointer %d is null", i);
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<float> img;
+    pack_images(h->cfg.n_classes, h->rows5, w, img);
+    CUDA_TRY(cudaMemcpy(h->wimg, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->loaded = true;
+    return WRNN_OK;
+}
+
+// ---- step loop launch --------------------------------------------------------------------------
+static int32_t launch_chunk(wrnn_handle *h, KParams &p, cudaStream_t st, bool probe)
+{
+    void *args[] = {&p};
+    CUDA_TRY(cudaMemsetAsync(h->flags, 0, (size_t)MAXG * NEXCH * NCTA * sizeof(unsigned), st));
+    CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    CUDA_TRY(cudaLaunchCooperativeKernel(probe ? (const void *)wavernn_exchange_probe_kernel : (const void *)wavernn_persistent_kernel,
+                                         dim3(NCTA), dim3(NTHREADS), args, (size_t)h->smem_bytes, st));
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms += ms;
+    h->launches += 1;
+    int status[4];
+    CUDA_TRY(cudaMemcpy(status, h->status, sizeof status, cudaMemcpyDeviceToHost));
+    h->last_status = status[0];
+    if (status[0] != 0) return fail(WRNN_ERR_TIMEOUT, "persistent kernel watchdog fired (status %d): a grid-level exchange never completed", status[0]);
+    return WRNN_OK;
+}
+
+static void fill_common(wrnn_handle *h, KParams &p)
+{
+    memset(&p, 0, sizeof p);
+    p.wimg = h->wimg;
+    p.xb = h->xb;
+    p.flags = h->flags;
+    p.status = h->status;
+    p.C = h->cfg.n_classes;
+    p.mode = h->cfg.mode;
+    p.rows5 = h->rows5;
+    p.nprod5 = h->nprod5;
+    p.n_u = h->n_u;
+    p.feat = h->cfg.feat_dims;
+    p.auxw = 4 * h->cfg.aux_dims;
+}
+
+extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const float *aux, int64_t cond_rows,
+                                       const int64_t *fold_start, const int64_t *fold_limit,
+                                       int32_t num_folds, int32_t steps,
+                                       const float *uniforms, uint64_t seed,
+                                       const float *forced_x, float *logits_out,
+                                       float *samples_out, int32_t *labels_out, void *stream)
+{
+    if (!h) return fail(WRNN_ERR_INVALID, "null handle");
+    if (!h->loaded) return fail(WRNN_ERR_STATE, "wrnn_load_weights has not been called");
+    if (!mels || !aux || !fold_start || !fold_limit || !samples_out) return fail(WRNN_ERR_INVALID, "null pointer argument");
+    if (num_folds <= 0 || steps <= 0) return fail(WRNN_ERR_INVALID, "num_folds (%d) and steps (%d) must be positive", num_folds, steps);
+    if (((uintptr_t)mels | (uintptr_t)aux) & 15) return fail(WRNN_ERR_INVALID, "conditioning pointers must be 16-byte aligned");
+    for (int b = 0; b < num_folds; ++b) {
+        if (fold_start[b] < 0 || fold_limit[b] > cond_rows || fold_limit[b] < 0)
+            return fail(WRNN_ERR_INVALID, "fold %d: start %lld / limit %lld outside [0, %lld]", b, (long long)fold_start[b], (long long)fold_limit[b], (long long)cond_rows);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (num_folds > h->fold_cap) {
+        cudaFree(h->fold_dev);
+        h->fold_dev = nullptr;
+        CUDA_TRY(cudaMalloc(&h->fold_dev, (size_t)2 * num_folds * sizeof(long long)));
+        h->fold_cap = num_folds;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->fold_dev, fold_start, (size_t)num_folds * sizeof(long long), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(h->fold_dev + h->fold_cap, fold_limit, (size_t)num_folds * sizeof(long long), cudaMemcpyHostToDevice, st));
+
+    h->last_ms = 0.f;
+    const int max_chunk = MAXG * BT;
+    for (int b0 = 0; b0 < num_folds; b0 += max_chunk) {
+        const int nb = num_folds - b0 < max_chunk ? num_folds - b0 : max_chunk;
+        KParams p;
+        fill_common(h, p);
+        p.mels = mels;
+        p.aux = aux;
+        p.fold_start = h->fold_dev;
+        p.fold_limit = h->fold_dev + h->fold_cap;
+        p.uniforms = uniforms;
+        p.forced_x = forced_x;
+        p.logits_out = logits_out;
+        p.samples_out = samples_out;
+        p.labels_out = labels_out;
+        p.seed = seed;
+        p.B = num_folds;
+        p.S = steps;
+        p.G = (nb + BT - 1) / BT;
+        int next = b0;
+        for (int g = 0; g < p.G; ++g) {           // balanced groups: sizes differ by at most one
+            const int nf = nb / p.G + (g < nb % p.G ? 1 : 0);
+            p.group_fold0[g] = next;
+            p.group_nf[g] = nf;
+            next += nf;
+        }
+        int32_t rc = launch_chunk(h, p, st, false);
+        if (rc) return rc;
+    }
+    return WRNN_OK;
+}
+
+extern "C" int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *usec_per_exchange)
+{
+    if (!h || !usec_per_exchange || iters <= 0) return fail(WRNN_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    KParams p;
+    fill_common(h, p);
+    p.G = 1;
+    p.probe_iters = iters;
+    h->last_ms = 0.f;
+    int32_t rc = launch_chunk(h, p, nullptr, true);   // warm-up
+    if (rc) return rc;
+    h->last_ms = 0.f;
+    rc = launch_chunk(h, p, nullptr, true);
+    if (rc) return rc;
+    *usec_per_exchange = h->last_ms * 1000.f / (float)iters;
+    return WRNN_OK;
+}
+
+extern "C" int32_t wrnn_get_info(wrnn_handle *h, wrnn_info *out)
+{
+    if (!h || !out) return fail(WRNN_ERR_INVALID, "null argument");
+    out->ctas = NCTA;
+    out->threads = NTHREADS;
+    out->smem_bytes = h->smem_bytes;
+    out->folds_per_group = BT;
+    out->max_folds_per_launch = MAXG * BT;
+    out->exchanges_per_step = NEXCH;
+    out->sm_count = h->sm_count;
+    out->launches = h->launches;
+    out->epilogue_launches = g_epilogue_launches;
+    out->last_kernel_status = h->last_status;
+    out->last_kernel_ms = h->last_ms;
+    return WRNN_OK;
+}
+
+// ---- epilogue ----------------------------------------------------------------------------------
+// numpy.linspace(start, stop, num): y_i = i*step + start with two roundings, last element = stop
+static void np_linspace(double start, double stop, int64_t num, double *y)
+{
+    if (num <= 0) return;
+    const int64_t div = num - 1;
+    const double delta = stop - start;
+    if (div > 0) {
+        const double step = delta / (double)div;
+        for (int64_t i = 0; i < num; ++i) {
+            volatile double m = (double)i * step;
+            y[i] = m + start;
+        }
+        y[num - 1] = stop;
+    } else {
+        volatile double m = 0.0 * delta;
+        y[0] = m + start;
+    }
+}
+
+// One thread per output sample.  fatchord_version.py:222-237 + utility/dsp.py:100-105.
+__global__ void xfade_unfold_kernel(const float *__restrict__ samples, int B, int S, int batched, int overlap,
+                                    const double *__restrict__ fade_in, const double *__restrict__ fade_out,
+                                    const double *__restrict__ tail, int mu_classes, long long wave_len, int tail_len,
+                                    double *__restrict__ out)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= wave_len) return;
+    double v;
+    if (batched) {
+        const long long hop = (long long)S - overlap;            // target + overlap
+        long long hi = p / hop;
+        if (hi > B - 1) hi = B - 1;
+        v = 0.0;                                                  // np.zeros(total_len), :375
+        for (long long i = hi - 1; i <= hi; ++i) {                // ascending fold order, :378-381
+            if (i < 0) continue;
+            const long long s = p - i * hop;
+            if (s < 0 || s >= S) continue;
+            double y = (double)samples[i * S + s];                // .astype(np.float64), :224
+            if (s < overlap) y = __dmul_rn(y, fade_in[s]);        // :372
+            if (s >= S - overlap) y = __dmul_rn(y, fade_out[s - (S - overlap)]);   // :373
+            v = __dadd_rn(v, y);
+        }
+    } else
+        v = (double)samples[p];                                   // output[0], :229
+    if (mu_classes) {                                             // decode_mu_law, dsp.py:103-104
+        const double mu = (double)(mu_classes - 1);
+        const double sgn = v > 0.0 ? 1.0 : (v < 0.0 ? -1.0 : 0.0);
+        const double q = __ddiv_rn(sgn, mu);
+        const double pw = pow(1.0 + mu, fabs(v));
+        v = __dmul_rn(q, __dsub_rn(pw, 1.0));
+    }
+    if (p >= wave_len - tail_len) v = __dmul_rn(v, tail[p - (wave_len - tail_len)]);   // :235-237
+    out[p] = v;
+}
+
+static thread_local double *t_tables_dev = nullptr;
+static thread_local int t_overlap = -1, t_tail = -1, t_device = -1;
+
+extern "C" int32_t wrnn_xfade_unfold(const float *samples, int32_t num_folds, int32_t steps,
+                                     int32_t batched, int32_t overlap, int32_t mu_law_classes,
+                                     int64_t wave_len, int32_t tail_fade, double *out, void *stream)
+{
+    if (!samples || !out) return fail(WRNN_ERR_INVALID, "null pointer argument");
+    if (num_folds <= 0 || steps <= 0 || wave_len <= 0) return fail(WRNN_ERR_INVALID, "num_folds, steps and wave_len must be positive");
+    if (tail_fade < 0 || tail_fade > wave_len)
+        return fail(WRNN_ERR_INVALID, "tail fade of %d samples does not fit wave_len %lld (reference: broadcast ValueError, needs T >= 21 frames)", tail_fade, (long long)wave_len);
+    int64_t total;
+    if (batched) {
+        if (overlap <= 0) return fail(WRNN_ERR_INVALID, "batched crossfade needs overlap > 0 (reference: y[:, -0:] broadcast error)");
+        if (steps < 2 * overlap) return fail(WRNN_ERR_INVALID, "steps (%d) < 2 * overlap (%d)", steps, overlap);
+        total = (int64_t)num_folds * (steps - overlap) + overlap;
+    } else {
+        if (num_folds != 1) return fail(WRNN_ERR_INVALID, "unbatched epilogue takes exactly one fold");
+        total = steps;
+        overlap = 0;
+    }
+    if (wave_len > total) return fail(WRNN_ERR_INVALID, "wave_len %lld exceeds the unfolded length %lld", (long long)wave_len, (long long)total);
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (t_overlap != overlap || t_tail != tail_fade || t_device != dev) {
+        // fade tables, fatchord_version.py:357-369 and :235
+        const int sil = overlap / 2, fl = overlap - sil;
+        std::vector<double> tab((size_t)2 * overlap + tail_fade + 1, 0.0), t((size_t)fl + 1);
+        np_linspace(-1.0, 1.0, fl, t.data());
+        for (int i = 0; i < fl; ++i) {
+            volatile double a = 1.0 + t[i], b = 0.5 * a, c = 1.0 - t[i], d = 0.5 * c;
+            tab[sil + i] = sqrt(b);               // fade_in  = [0]*sil ++ sqrt(.5(1+t))
+            tab[overlap + i] = sqrt(d);           // fade_out = sqrt(.5(1-t)) ++ [0]*sil
+        }
+        np_linspace(1.0, 0.0, tail_fade, tab.data() + 2 * overlap);
+        CUDA_TRY(cudaStreamSynchronize(st));      // previous users of the cached table are done
+        if (t_tables_dev) cudaFree(t_tables_dev);
+        t_tables_dev = nullptr;
+        CUDA_TRY(cudaMalloc(&t_tables_dev, tab.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(t_tables_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+        t_overlap = overlap;
+        t_tail = tail_fade;
+        t_device = dev;
+    }
+    const int threads = 256;
+    const long long blocks = (wave_len + threads - 1) / threads;
+    xfade_unfold_kernel<<<(unsigned)blocks, threads, 0, st>>>(samples, num_folds, steps, batched, overlap, t_tables_dev,
+                                                              t_tables_dev + overlap, t_tables_dev + 2 * overlap,
+                                                              mu_law_classes, wave_len, tail_fade, out);
+    CUDA_TRY(cudaGetLastError());
+    g_epilogue_launches += 1;
+    return WRNN_OK;
+}

@@ -1,0 +1,844 @@
+// Persistent sm_100a kernel for the WaveRNN step loop (reference: WaveRNN/models/
+// fatchord_version.py:171-222).  See DESIGN.md for the derivation; summary:
+//
+//  * 128 CTAs (one per SM, cooperative launch), each owns 4 of the 512 hidden units of every
+//    layer; its rows of every weight matrix stay resident in shared memory for all steps.
+//  * Folds advance in groups of 8.  A group goes through 5 grid-level exchanges per step
+//    (h1 | h2,s | y1 | y2 | logits): a CTA publishes one 128-byte line + a flag, polls the
+//    128 flags, gathers the 16 KiB vector from L2.  Groups are interleaved in a static order
+//    so one group's exchange latency hides behind the other groups' mat-vecs.
+//  * The input layer I and every conditioning term are folded algebraically into the
+//    downstream layers at load time (host, fp64), so the recurrence only multiplies
+//    h1, h2, s=h1+h2, y1, y2; conditioning projections for step t+1 are computed during
+//    step t from TMA-staged rows of the UNFOLDED conditioning (fold gather fused).
+//  * Sampling (softmax inverse-CDF / mixture-of-logistics) is done redundantly by every
+//    CTA from the gathered logits, so no broadcast exchange is needed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wrnn {
+
+constexpr int HID = 512;          // rnn_dims == fc_dims
+constexpr int NCTA = 128;         // CTAs; UNITS hidden units each
+constexpr int UNITS = 4;
+constexpr int BT = 8;             // folds per group (one 32-byte row of an exchanged vector)
+constexpr int NTHREADS = 512;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int MAXG = 8;           // groups per launch -> 64 folds
+constexpr int VEC = HID * BT;     // floats of one exchanged vector (16 KiB)
+constexpr int ITEM = 4 * 32 * 4;  // floats of one weight item image: 4 rows x 128 k
+constexpr int NEXCH = 5;
+constexpr int CONDK = 256;        // padded conditioning length (80 mel + 4*32 aux = 208)
+constexpr int COND_ITEMS = 12;
+
+// ---- per-CTA weight image (floats) --------------------------------------------------------
+constexpr int W_M2 = 0;                       // 24 rows: Wih2x gates (12) | Whh1 gates (12), x H1
+constexpr int W_M3 = W_M2 + 24 * HID;         // 16 rows: Wfc1x (4) x S | Whh2 gates (12) x H2
+constexpr int W_M4 = W_M3 + 16 * HID;         // 4 rows: Wfc2x x Y1
+constexpr int W_M5 = W_M4 + 4 * HID;          // rows5 rows: Wfc3 x Y2
+__host__ __device__ constexpr int w_mc(int rows5) { return W_M5 + rows5 * HID; }           // 12 cond items
+__host__ __device__ constexpr int w_small(int rows5) { return w_mc(rows5) + COND_ITEMS * ITEM; }
+// small vectors (offsets inside the small block)
+constexpr int SV_U1 = 0, SV_B1 = 12, SV_BHH1 = 24, SV_U2 = 36, SV_B2 = 48, SV_BHH2 = 60,
+              SV_U3 = 72, SV_B3 = 76, SV_B4 = 80, SV_B5 = 84, SV_SIZE = 128;
+__host__ __device__ constexpr int w_total(int rows5) { return w_small(rows5) + SV_SIZE; }
+
+// ---- per-group private state (floats) -----------------------------------------------------
+constexpr int PG_GH1 = 0, PG_GH2 = 96, PG_P1 = 192, PG_P2 = 288, PG_P3 = 384, PG_P4 = 416,
+              PG_H1 = 448, PG_H2 = 480, PG_X = 512, PG_U = 520, PG_FX = 608, PG_SIZE = 640;
+
+// ---- shared memory map (floats) -----------------------------------------------------------
+struct SmemMap {
+    int w, stage, cx, cstage, part, priv, samp, mbar, total;
+};
+__host__ __device__ inline SmemMap smem_map(int rows5)
+{
+    SmemMap m;
+    m.w = 0;
+    m.stage = m.w + w_total(rows5);
+    m.cx = m.stage + 2 * VEC;
+    m.cstage = m.cx + CONDK * BT;
+    m.part = m.cstage + 2 * BT * 208;
+    m.priv = m.part + NWARPS * 32;
+    m.samp = m.priv + MAXG * PG_SIZE;
+    m.mbar = m.samp + 1024;
+    m.total = m.mbar + 8;
+    return m;
+}
+
+struct KParams {
+    const float *wimg;                 // [NCTA][w_total]
+    const float *mels, *aux;           // unfolded conditioning [rows, 80] / [rows, 128]
+    const long long *fold_start, *fold_limit;
+    const float *uniforms, *forced_x;
+    float *logits_out, *samples_out;
+    int *labels_out;
+    float *xb;                         // [G][xb_group]  exchange buffers
+    unsigned *flags;                   // [G][NEXCH][NCTA]
+    int *status;
+    unsigned long long seed;
+    int B, S, G, C, mode, rows5, nprod5, n_u;   // n_u: uniforms per fold-step (1 RAW, 11 MOL)
+    int feat, auxw;                    // 80, 128
+    int group_fold0[MAXG], group_nf[MAXG];
+    int probe_iters;
+};
+constexpr int XB_H1 = 0, XB_H2 = VEC, XB_S = 2 * VEC, XB_Y1 = 3 * VEC, XB_Y2 = 4 * VEC, XB_LG = 5 * VEC;
+__host__ __device__ constexpr int xb_group(int cpad) { return 5 * VEC + cpad * BT; }
+
+// ============================================================================================
+// device helpers
+// ============================================================================================
+__device__ __forceinline__ float4 ldg_cg4(const float *p)
+{
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 ld_flags4(const unsigned *p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_flag(unsigned *p, unsigned v)
+{
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_cg(float *p, float v)
+{
+    asm volatile("st.global.cg.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// physical index of (k, fold f) inside an exchanged vector: 32-byte rows, the two 16-byte
+// halves swapped on every other group of 4 rows so that 8 lanes reading 16 B at a 32 B
+// stride touch all 32 banks.
+__device__ __forceinline__ int xidx(int k, int f) { return k * BT + (f ^ (((k >> 2) & 1) << 2)); }
+
+// mbarrier + 1-D bulk TMA (cp.async.bulk) -- conditioning rows are staged with these
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Philox4x32-10 (Salmon et al. 2011): counter-based RNG for the in-kernel uniforms
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
+{
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+__device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// Poll `nprod` (<=128) producer flags until all reach `epoch`.  Warp 0 only.  false = watchdog.
+__device__ __forceinline__ bool wait_flags(const unsigned *flags, int nprod, unsigned epoch, int lane)
+{
+    const bool mine = lane * 4 < nprod;
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        bool ok = true;
+        if (mine) {
+            uint4 v = ld_flags4(flags + lane * 4);
+            ok = (v.x >= epoch) & (v.y >= epoch) & (v.z >= epoch) & (v.w >= epoch);
+        }
+        if (__all_sync(0xffffffffu, ok)) {
+            fence_gpu();
+            return true;
+        }
+    }
+    return false;
+}
+
+// Gather `n4` float4 from an exchange buffer (L2; never L1) into shared memory.  All threads.
+__device__ __forceinline__ void gather_vec(float *dst, const float *src, int n4, int tid)
+{
+    if (n4 == VEC / 4) {
+        float4 a = ldg_cg4(src + 4 * tid);
+        float4 b = ldg_cg4(src + 4 * (tid + NTHREADS));
+        *reinterpret_cast<float4 *>(dst + 4 * tid) = a;
+        *reinterpret_cast<float4 *>(dst + 4 * (tid + NTHREADS)) = b;
+    } else {
+        for (int i = tid; i < n4; i += NTHREADS) {
+            float4 a = ldg_cg4(src + 4 * i);
+            *reinterpret_cast<float4 *>(dst + 4 * i) = a;
+        }
+    }
+}
+
+// One work item: acc[4 rows][8 folds] += W[4][128 k] * X[128 k][8 folds].
+// wimg: item image [4][32 lanes] float4, element i of lane l = W[row][kbase + l + 32 i].
+// xs: exchanged vector in shared memory; lane l consumes k = kbase + l + 32 i.
+__device__ __forceinline__ void item_fma(const float *wimg, const float *xs, int kbase, int lane, float (&acc)[4][BT])
+{
+    float4 w[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const float4 *>(wimg + (r * 32 + lane) * 4);
+    const int sw = ((lane >> 2) & 1) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float *xp = xs + (kbase + lane + 32 * i) * BT;
+        const float4 lo = *reinterpret_cast<const float4 *>(xp + sw);        // folds 0..3
+        const float4 hi = *reinterpret_cast<const float4 *>(xp + (4 - sw));  // folds 4..7
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float wv = (i == 0) ? w[r].x : (i == 1) ? w[r].y : (i == 2) ? w[r].z : w[r].w;
+            acc[r][0] = fmaf(wv, lo.x, acc[r][0]);
+            acc[r][1] = fmaf(wv, lo.y, acc[r][1]);
+            acc[r][2] = fmaf(wv, lo.z, acc[r][2]);
+            acc[r][3] = fmaf(wv, lo.w, acc[r][3]);
+            acc[r][4] = fmaf(wv, hi.x, acc[r][4]);
+            acc[r][5] = fmaf(wv, hi.y, acc[r][5]);
+            acc[r][6] = fmaf(wv, hi.z, acc[r][6]);
+            acc[r][7] = fmaf(wv, hi.w, acc[r][7]);
+        }
+    }
+}
+
+// Cross-lane reduce-scatter of the 32 accumulators: lane l returns the warp-wide sum of
+// acc[l >> 3][l & 7] (31 shuffles instead of 160).
+__device__ __forceinline__ float reduce_scatter32(float (&acc)[4][BT], int lane)
+{
+    float v[32];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int f = 0; f < BT; ++f) v[r * BT + f] = acc[r][f];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const float send = upper ? v[j] : v[j + off];
+            const float keep = upper ? v[j + off] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[4][BT])
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int f = 0; f < BT; ++f) acc[r][f] = 0.f;
+}
+
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+// Publish this CTA's 4 x 8 values of one exchanged vector (one 128-byte line) and raise its flag.
+// Warp 0 only; lane = unit*8 + fold.
+__device__ __forceinline__ void publish_line(float *vec, int cta, int lane, float val)
+{
+    const int k = UNITS * cta + (lane >> 3);
+    st_cg(vec + xidx(k, lane & 7), val);
+}
+__device__ __forceinline__ void raise_flag(unsigned *flag, unsigned epoch, int lane)
+{
+    __syncwarp();
+    if (lane == 0) {
+        fence_gpu();
+        st_flag(flag, epoch);
+    }
+}
+
+// ============================================================================================
+// the persistent kernel
+// ============================================================================================
+struct Ctx {
+    const KParams *p;
+    float *sm;
+    SmemMap m;
+    int tid, lane, warp, cta;
+    int cond_visit;      // running count of conditioning visits (selects staging buffer / parity)
+};
+
+__device__ __forceinline__ float *priv(const Ctx &c, int g) { return c.sm + c.m.priv + g * PG_SIZE; }
+__device__ __forceinline__ const float *small(const Ctx &c) { return c.sm + c.m.w + w_small(c.p->rows5); }
+__device__ __forceinline__ unsigned *flag_base(const Ctx &c, int g, int e) { return c.p->flags + ((size_t)g * NEXCH + e) * NCTA; }
+__device__ __forceinline__ float *xb_base(const Ctx &c, int g)
+{
+    return c.p->xb + (size_t)g * xb_group(c.p->rows5 * c.p->nprod5);
+}
+
+// Block until the flags of (g, e) reach `epoch`; returns false on watchdog (CTA-uniform).
+__device__ __forceinline__ bool cta_wait(Ctx &c, int g, int e, int nprod, unsigned epoch)
+{
+    int *abort_flag = reinterpret_cast<int *>(c.sm + c.m.mbar + 6);
+    if (c.warp == 0) {
+        bool ok = wait_flags(flag_base(c, g, e), nprod, epoch, c.lane);
+        if (!ok && c.lane == 0) {
+            *abort_flag = 1;
+            atomicExch(c.p->status, -4);
+        }
+    }
+    __syncthreads();
+    return *abort_flag == 0;
+}
+
+// Issue the TMA row copies of the conditioning for conditioning-visit v (group v % G, step v / G)
+// into staging buffer v & 1.  Called by ALL lanes of one warp: lane f < 8 copies fold f's two
+// rows (mel 320 B + aux 512 B).  Rows past fold_limit are the fold padding (zeros): they are
+// not copied, their bit stays clear in the validity mask and cond_visit writes zeros instead.
+__device__ __forceinline__ void cond_issue(Ctx &c, int v)
+{
+    const KParams &p = *c.p;
+    const int g = v % p.G, step = v / p.G;
+    if (step >= p.S) return;
+    float *buf = c.sm + c.m.cstage + (v & 1) * (BT * 208);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(c.sm + c.m.mbar) + (v & 1);
+    int *mask = reinterpret_cast<int *>(c.sm + c.m.mbar + 4) + (v & 1);
+    const int f = c.lane;
+    bool valid = false;
+    long long row = 0;
+    if (f < p.group_nf[g]) {
+        const int b = p.group_fold0[g] + f;
+        row = p.fold_start[b] + step;
+        valid = row < p.fold_limit[b];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (c.lane == 0) {
+        *mask = (int)m;
+        mbar_expect_tx(bar, (unsigned)(__popc(m) * (p.feat + p.auxw) * 4));
+    }
+    __syncwarp();
+    if (valid) {
+        tma_bulk_g2s(buf + f * 208, p.mels + row * p.feat, (unsigned)(p.feat * 4), bar);
+        tma_bulk_g2s(buf + f * 208 + p.feat, p.aux + row * p.auxw, (unsigned)(p.auxw * 4), bar);
+    }
+}
+
+// Wait for conditioning visit v, transpose it into the [k][8] exchange layout (cx), and issue
+// the copies for visit v+1.  All threads; caller syncs before the items read cx.
+__device__ __forceinline__ void cond_visit(Ctx &c)
+{
+    const KParams &p = *c.p;
+    const int v = c.cond_visit++;
+    const int step = v / p.G;
+    if (step >= p.S) return;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(c.sm + c.m.mbar) + (v & 1);
+    const unsigned parity = (unsigned)((v >> 1) & 1);
+    while (!mbar_try_wait(bar, parity)) {
+    }
+    const int mask = reinterpret_cast<const int *>(c.sm + c.m.mbar + 4)[v & 1];
+    const float *buf = c.sm + c.m.cstage + (v & 1) * (BT * 208);
+    float *cx = c.sm + c.m.cx;
+    for (int i = c.tid; i < 208 * BT; i += NTHREADS) {
+        const int f = i / 208, k = i - f * 208;
+        cx[xidx(k, f)] = ((mask >> f) & 1) ? buf[i] : 0.f;
+    }
+    __syncthreads();                 // staging buffer (v+1)&1 was consumed one visit ago; cx complete
+    if (c.warp == NWARPS - 1) cond_issue(c, v + 1);
+}
+
+// The 12 conditioning items (warps 4..15) and their finalisation into P1..P4 of group g.
+__device__ __forceinline__ void cond_items(Ctx &c, int w)
+{
+    // item order: 0-2 P1 (chunk A) | 3-8 P2 (rg*2 + chunk) | 9,10 P3 (A,B) | 11 P4 (B)
+    const int it = w - 4;
+    const int chunk = (it < 3) ? 0 : (it < 9) ? ((it - 3) & 1) : (it == 9) ? 0 : 1;
+    float acc[4][BT];
+    zero_acc(acc);
+    item_fma(c.sm + c.m.w + w_mc(c.p->rows5) + it * ITEM, c.sm + c.m.cx, chunk * 128, c.lane, acc);
+    c.sm[c.m.part + w * 32 + c.lane] = reduce_scatter32(acc, c.lane);
+}
+__device__ __forceinline__ void cond_finalize(Ctx &c, int g, int w)
+{
+    float *pg = priv(c, g);
+    const float *part = c.sm + c.m.part;
+    const int l = c.lane;
+    if (w >= 1 && w <= 3) pg[PG_P1 + (w - 1) * 32 + l] = part[(4 + (w - 1)) * 32 + l];
+    else if (w >= 4 && w <= 6) pg[PG_P2 + (w - 4) * 32 + l] = part[(4 + 3 + 2 * (w - 4)) * 32 + l] + part[(4 + 4 + 2 * (w - 4)) * 32 + l];
+    else if (w == 7) pg[PG_P3 + l] = part[(4 + 9) * 32 + l] + part[(4 + 10) * 32 + l];
+    else if (w == 8) pg[PG_P4 + l] = part[(4 + 11) * 32 + l];
+}
+
+// Fetch the uniforms / forced value that step `step` of group g will need at sampling time.
+__device__ __forceinline__ void prefetch_draws(Ctx &c, int g, int step)
+{
+    const KParams &p = *c.p;
+    float *pg = priv(c, g);
+    const int nu = p.n_u;
+    for (int i = c.lane; i < BT * nu; i += 32) {
+        const int f = i / nu, j = i - f * nu;
+        float u = 0.f;
+        if (f < p.group_nf[g]) {
+            const int b = p.group_fold0[g] + f;
+            if (p.uniforms) u = p.uniforms[((size_t)step * p.B + b) * nu + j];
+            else {
+                uint4 r = philox4x32_10(make_uint4((unsigned)step, (unsigned)b, (unsigned)(j >> 2), 0u),
+                                        make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
+                const unsigned x = ((j & 3) == 0) ? r.x : ((j & 3) == 1) ? r.y : ((j & 3) == 2) ? r.z : r.w;
+                u = u01(x);
+            }
+        }
+        pg[PG_U + f * 11 + j] = u;
+    }
+    if (c.lane < BT) {
+        float fx = 0.f;
+        if (p.forced_x && c.lane < p.group_nf[g]) fx = p.forced_x[(size_t)step * p.B + p.group_fold0[g] + c.lane];
+        pg[PG_FX + c.lane] = fx;
+    }
+}
+
+// ---- sampling (all threads): logits of step s are in c.sm[stage]; writes x into priv ---------
+__device__ __forceinline__ void sample_raw(Ctx &c, int g, int s)
+{
+    const KParams &p = *c.p;
+    const float *lg = c.sm + c.m.stage;
+    float *sc = c.sm + c.m.samp;                 // [0,256) block max, [256,512) block sum, 512.. owner, 520.. thr, 528.. label
+    float *pg = priv(c, g);
+    const int lane = c.lane, f = lane & 7, cs = lane >> 3;
+    const int nblk = p.C >> 5;
+    float e[2][8];
+#pragma unroll
+    for (int bi = 0; bi < 2; ++bi) {
+        const int blk = c.warp + bi * NWARPS;
+        if (blk < nblk) {
+            float v[8], bm = -INFINITY;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                v[m] = lg[xidx(32 * blk + 4 * m + cs, f)];
+                bm = fmaxf(bm, v[m]);
+            }
+            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
+            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+            float ls = 0.f;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) {
+                e[bi][m] = expf(v[m] - bm);
+                ls += e[bi][m];
+            }
+            ls += __shfl_xor_sync(0xffffffffu, ls, 8);
+            ls += __shfl_xor_sync(0xffffffffu, ls, 16);
+            if (cs == 0) {
+                sc[blk * 8 + f] = bm;
+                sc[256 + blk * 8 + f] = ls;
+            }
+        }
+    }
+    __syncthreads();
+    if (c.warp == 0) {
+        // lane (f, cs) owns blocks cs*8 .. cs*8+7 (block order == class order)
+        float bmx[8], bsum[8], M = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int blk = cs * 8 + j;
+            bmx[j] = (blk < nblk) ? sc[blk * 8 + f] : -INFINITY;
+            bsum[j] = (blk < nblk) ? sc[256 + blk * 8 + f] : 0.f;
+            M = fmaxf(M, bmx[j]);
+        }
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 8));
+        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
+        float scale[8], pre[8], run = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            scale[j] = (cs * 8 + j < nblk) ? expf(bmx[j] - M) : 0.f;
+            pre[j] = run;                       // scaled mass of this lane's blocks before block j
+            run += bsum[j] * scale[j];
+        }
+        // exclusive scan of `run` over the four cs lanes of this fold
+        const float r1 = __shfl_up_sync(0xffffffffu, run, 8), r2 = __shfl_up_sync(0xffffffffu, run, 16),
+                    r3 = __shfl_up_sync(0xffffffffu, run, 24);
+        const float base = (cs >= 1 ? r1 : 0.f) + (cs >= 2 ? r2 : 0.f) + (cs >= 3 ? r3 : 0.f);
+        const float tot = __shfl_sync(0xffffffffu, base + run, 24 + f);
+        const float thr = pg[PG_U + f * 11] * tot;
+        int own = 1 << 20;
+        float thr_local = INFINITY;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+            const int blk = cs * 8 + j;
+            if (blk < nblk && base + pre[j] + bsum[j] * scale[j] > thr) {
+                own = blk;
+                thr_local = (thr - (base + pre[j])) / scale[j];
+            }
+        }
+        // first owning block over the cs lanes
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+            const int o2 = __shfl_xor_sync(0xffffffffu, own, off);
+            const float t2 = __shfl_xor_sync(0xffffffffu, thr_local, off);
+            if (o2 < own) {
+                own = o2;
+                thr_local = t2;
+            }
+        }
+        if (cs == 0) {
+            if (own >= nblk) {                   // u * total beyond the last prefix: clamp to the last class
+                own = nblk - 1;
+                thr_local = INFINITY;
+            }
+            sc[512 + f] = __int_as_float(own);
+            sc[520 + f] = thr_local;
+        }
+    }
+    __syncthreads();
+    {
+        const int own = __float_as_int(sc[512 + f]);
+        const float thr_local = sc[520 + f];
+#pragma unroll
+        for (int bi = 0; bi < 2; ++bi) {
+            const int blk = c.warp + bi * NWARPS;
+            if (blk < nblk) {                    // warp-uniform
+                float rowbase = 0.f;
+                int cnt = 0;
+#pragma unroll
+                for (int m = 0; m < 8; ++m) {
+                    const float a1 = __shfl_up_sync(0xffffffffu, e[bi][m], 8), a2 = __shfl_up_sync(0xffffffffu, e[bi][m], 16),
+                                a3 = __shfl_up_sync(0xffffffffu, e[bi][m], 24);
+                    const float incl = ((cs >= 3 ? a3 : 0.f) + (cs >= 2 ? a2 : 0.f)) + (cs >= 1 ? a1 : 0.f) + e[bi][m];
+                    float rs = e[bi][m] + __shfl_xor_sync(0xffffffffu, e[bi][m], 8);
+                    rs += __shfl_xor_sync(0xffffffffu, rs, 16);
+                    cnt += (rowbase + incl <= thr_local) ? 1 : 0;
+                    rowbase += rs;
+                }
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
+                if (cs == 0 && own == blk) {
+                    int k = 32 * blk + cnt;
+                    k = k > p.C - 1 ? p.C - 1 : k;
+                    sc[528 + f] = __int_as_float(k);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (c.warp == 0 && lane < BT) {
+        const int k = __float_as_int(sc[528 + lane]);
+        // 2 * k.float() / (C - 1.) - 1.  (fatchord_version.py:214), three separately rounded fp32 ops
+        const float sample = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, (float)k), (float)p.C - 1.0f), 1.0f);
+        if (lane < p.group_nf[g] && c.cta == (s * p.G + g) % NCTA) {
+            const int b = p.group_fold0[g] + lane;
+            p.samples_out[(size_t)b * p.S + s] = sample;
+            if (p.labels_out) p.labels_out[(size_t)b * p.S + s] = k;
+        }
+        pg[PG_X + lane] = p.forced_x ? pg[PG_FX + lane] : sample;
+    }
+}
+
+__device__ __forceinline__ void sample_mol(Ctx &c, int g, int s)
+{
+    // sample_from_discretized_mix_logistic, utility/distribution.py:87-123
+    const KParams &p = *c.p;
+    const float *lg = c.sm + c.m.stage;
+    float *pg = priv(c, g);
+    if (c.warp == 0) {
+        const int lane = c.lane, f = lane & 7, cs = lane >> 3;
+        const int nr = p.C / 3;
+        float best = -INFINITY;
+        int arg = 1 << 20;
+        for (int i = cs; i < nr; i += 4) {
+            const float u = (float)(1e-5 + ((1.0 - 1e-5) - 1e-5) * (double)pg[PG_U + f * 11 + i]);
+            const float t = lg[xidx(i, f)] - logf(-logf(u));
+            if (t > best) {
+                best = t;
+                arg = i;
+            }
+        }
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+            const float b2 = __shfl_xor_sync(0xffffffffu, best, off);
+            const int a2 = __shfl_xor_sync(0xffffffffu, arg, off);
+            if (b2 > best || (b2 == best && a2 < arg)) {
+                best = b2;
+                arg = a2;
+            }
+        }
+        if (cs == 0) {
+            const float mean = lg[xidx(nr + arg, f)];
+            const float ls = fmaxf(lg[xidx(2 * nr + arg, f)], -32.23619130191664f);
+            const float u2 = (float)(1e-5 + ((1.0 - 1e-5) - 1e-5) * (double)pg[PG_U + f * 11 + nr]);
+            float x = mean + expf(ls) * (logf(u2) - logf(1.0f - u2));
+            x = fminf(fmaxf(x, -1.0f), 1.0f);
+            if (f < p.group_nf[g] && c.cta == (s * p.G + g) % NCTA) {
+                const int b = p.group_fold0[g] + f;
+                p.samples_out[(size_t)b * p.S + s] = x;
+                if (p.labels_out) p.labels_out[(size_t)b * p.S + s] = arg;
+            }
+            pg[PG_X + f] = p.forced_x ? pg[PG_FX + f] : x;
+        }
+    }
+}
+
+// logits_out[s][b][c] from the gathered logits (teacher-forced parity runs only)
+__device__ __forceinline__ void dump_logits(Ctx &c, int g, int s)
+{
+    const KParams &p = *c.p;
+    if (!p.logits_out || c.cta != (s * p.G + g) % NCTA) return;
+    const float *lg = c.sm + c.m.stage;
+    for (int f = 0; f < p.group_nf[g]; ++f) {
+        float *dst = p.logits_out + ((size_t)s * p.B + p.group_fold0[g] + f) * p.C;
+        for (int k = c.tid; k < p.C; k += NTHREADS) dst[k] = lg[xidx(k, f)];
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel(const KParams prm)
+{
+    extern __shared__ __align__(128) float sm[];
+    Ctx c;
+    c.p = &prm;
+    c.sm = sm;
+    c.m = smem_map(prm.rows5);
+    c.tid = threadIdx.x;
+    c.lane = c.tid & 31;
+    c.warp = c.tid >> 5;
+    c.cta = blockIdx.x;
+    c.cond_visit = 0;
+    const KParams &p = prm;
+    const int G = p.G, S = p.S;
+    const int lane = c.lane, w = c.warp;
+
+    // ---- prologue: resident weights, zero state, conditioning projections of step 0 ----------
+    {
+        const float4 *src = reinterpret_cast<const float4 *>(p.wimg + (size_t)c.cta * w_total(p.rows5));
+        float4 *dst = reinterpret_cast<float4 *>(sm + c.m.w);
+        for (int i = c.tid; i < w_total(p.rows5) / 4; i += NTHREADS) dst[i] = src[i];
+        for (int i = c.tid; i < CONDK * BT; i += NTHREADS) sm[c.m.cx + i] = 0.f;
+        for (int i = c.tid; i < MAXG * PG_SIZE; i += NTHREADS) sm[c.m.priv + i] = 0.f;
+        if (c.tid == 0) {
+            uint64_t *bar = reinterpret_cast<uint64_t *>(sm + c.m.mbar);
+            mbar_init(bar, 1);
+            mbar_init(bar + 1, 1);
+            *reinterpret_cast<int *>(sm + c.m.mbar + 6) = 0;
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        const float *sv = small(c);
+        for (int g = 0; g < G; ++g) {           // h = 0  =>  gh = b_hh  (fatchord_version.py:173-174)
+            float *pg = priv(c, g);
+            if (c.tid < 96) {
+                pg[PG_GH1 + c.tid] = sv[SV_BHH1 + (c.tid >> 3)];
+                pg[PG_GH2 + c.tid] = sv[SV_BHH2 + (c.tid >> 3)];
+            }
+        }
+        if (c.warp == NWARPS - 1) cond_issue(c, 0);
+        __syncthreads();
+        for (int g = 0; g < G; ++g) {
+            cond_visit(c);
+            if (w >= 4) cond_items(c, w);
+            __syncthreads();
+            cond_finalize(c, g, w);
+            if (w == 9) prefetch_draws(c, g, 0);
+        }
+        __syncthreads();
+    }
+
+    for (int t = 0; t <= S; ++t) {
+        const unsigned epoch = (unsigned)t + 1u;
+        // ================= SA: sample step t-1, then GRU1 of step t ============================
+        for (int g = 0; g < G; ++g) {
+            float *pg = priv(c, g);
+            float *xb = xb_base(c, g);
+            if (t > 0) {
+                if (!cta_wait(c, g, 4, p.nprod5, (unsigned)t)) return;
+                gather_vec(sm + c.m.stage, xb + XB_LG, p.rows5 * p.nprod5 * BT / 4, c.tid);
+                __syncthreads();
+                if (p.mode == 0) sample_raw(c, g, t - 1);
+                else sample_mol(c, g, t - 1);
+                dump_logits(c, g, t - 1);
+                __syncthreads();
+                if (w == 9 && t < S) prefetch_draws(c, g, t);       // draws for the sample of step t
+            }
+            if (t < S && w == 0) {
+                // rnn1 GRU cell for this CTA's 4 units x 8 folds (torch gate order r, z, n)
+                const float *sv = small(c);
+                const int u = lane >> 3, f = lane & 7;
+                const float x = pg[PG_X + f];
+                const float gr = pg[PG_P1 + lane] + x * sv[SV_U1 + u] + sv[SV_B1 + u];
+                const float gz = pg[PG_P1 + 32 + lane] + x * sv[SV_U1 + 4 + u] + sv[SV_B1 + 4 + u];
+                const float gn = pg[PG_P1 + 64 + lane] + x * sv[SV_U1 + 8 + u] + sv[SV_B1 + 8 + u];
+                const float r = sigmoidf_(gr + pg[PG_GH1 + lane]);
+                const float z = sigmoidf_(gz + pg[PG_GH1 + 32 + lane]);
+                const float n = tanhf(gn + r * pg[PG_GH1 + 64 + lane]);
+                const float h = (1.0f - z) * n + z * pg[PG_H1 + lane];
+                pg[PG_H1 + lane] = h;
+                publish_line(xb + XB_H1, c.cta, lane, h);
+                raise_flag(flag_base(c, g, 0) + c.cta, epoch, lane);
+            }
+        }
+        if (t == S) break;
+        // ================= S2: rnn2 input side + rnn1 hidden side of the next step ============
+        for (int g = 0; g < G; ++g) {
+            float *pg = priv(c, g);
+            float *xb = xb_base(c, g);
+            if (!cta_wait(c, g, 0, NCTA, epoch)) return;
+            gather_vec(sm + c.m.stage, xb + XB_H1, VEC / 4, c.tid);
+            __syncthreads();
+            if (w < 12) {
+                const int rg = w % 6, half = w / 6;
+                float acc[4][BT];
+                zero_acc(acc);
+                const float *wi = sm + c.m.w + W_M2 + (rg * 4 + half * 2) * ITEM;
+                item_fma(wi, sm + c.m.stage, (half * 2) * 128, lane, acc);
+                item_fma(wi + ITEM, sm + c.m.stage, (half * 2 + 1) * 128, lane, acc);
+                sm[c.m.part + w * 32 + lane] = reduce_scatter32(acc, lane);
+            }
+            __syncthreads();
+            const float *part = sm + c.m.part;
+            const float *sv = small(c);
+            if (w == 0) {
+                const int u = lane >> 3, f = lane & 7;
+                const float x = pg[PG_X + f];
+                float gi[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    gi[q] = (part[q * 32 + lane] + part[(6 + q) * 32 + lane]) + pg[PG_P2 + q * 32 + lane] + x * sv[SV_U2 + q * 4 + u] + sv[SV_B2 + q * 4 + u];
+                const float r = sigmoidf_(gi[0] + pg[PG_GH2 + lane]);
+                const float z = sigmoidf_(gi[1] + pg[PG_GH2 + 32 + lane]);
+                const float n = tanhf(gi[2] + r * pg[PG_GH2 + 64 + lane]);
+                const float h2 = (1.0f - z) * n + z * pg[PG_H2 + lane];
+                pg[PG_H2 + lane] = h2;
+                publish_line(xb + XB_H2, c.cta, lane, h2);
+                publish_line(xb + XB_S, c.cta, lane, pg[PG_H1 + lane] + h2);
+                raise_flag(flag_base(c, g, 1) + c.cta, epoch, lane);
+            } else if (w <= 3) {
+                const int q = w - 1;             // gh1 of the NEXT step: Whh1 . h1_t + b_hh1
+                pg[PG_GH1 + q * 32 + lane] = (part[(3 + q) * 32 + lane] + part[(9 + q) * 32 + lane]) + sv[SV_BHH1 + q * 4 + (lane >> 3)];
+            }
+        }
+        // ================= S3: fc1 + rnn2 hidden side of the next step =========================
+        for (int g = 0; g < G; ++g) {
+            float *pg = priv(c, g);
+            float *xb = xb_base(c, g);
+            if (!cta_wait(c, g, 1, NCTA, epoch)) return;
+            gather_vec(sm + c.m.stage, xb + XB_H2, VEC / 4, c.tid);
+            gather_vec(sm + c.m.stage + VEC, xb + XB_S, VEC / 4, c.tid);
+            __syncthreads();
+            {
+                float acc[4][BT];
+                zero_acc(acc);
+                if (w < 4) item_fma(sm + c.m.w + W_M3 + w * ITEM, sm + c.m.stage + VEC, w * 128, lane, acc);
+                else {
+                    const int rg = 1 + (w - 4) % 3, kc = (w - 4) / 3;
+                    item_fma(sm + c.m.w + W_M3 + (rg * 4 + kc) * ITEM, sm + c.m.stage, kc * 128, lane, acc);
+                }
+                sm[c.m.part + w * 32 + lane] = reduce_scatter32(acc, lane);
+            }
+            __syncthreads();
+            const float *part = sm + c.m.part;
+            const float *sv = small(c);
+            if (w == 0) {
+                const int u = lane >> 3, f = lane & 7;
+                float y = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + pg[PG_P3 + lane] + pg[PG_X + f] * sv[SV_U3 + u] + sv[SV_B3 + u];
+                y = fmaxf(y, 0.f);
+                publish_line(xb + XB_Y1, c.cta, lane, y);
+                raise_flag(flag_base(c, g, 2) + c.cta, epoch, lane);
+            } else if (w <= 3) {
+                const int q = w - 1;             // gh2 of the NEXT step
+                const int s0 = 4 + q;
+                pg[PG_GH2 + q * 32 + lane] = ((part[s0 * 32 + lane] + part[(s0 + 3) * 32 + lane]) + (part[(s0 + 6) * 32 + lane] + part[(s0 + 9) * 32 + lane])) + sv[SV_BHH2 + q * 4 + (lane >> 3)];
+            }
+        }
+        // ================= S4: fc2 + conditioning projections of step t+1 ======================
+        for (int g = 0; g < G; ++g) {
+            float *pg = priv(c, g);
+            float *xb = xb_base(c, g);
+            cond_visit(c);                       // stages cond(t+1) of this group, prefetches the next visit
+            if (!cta_wait(c, g, 2, NCTA, epoch)) return;
+            gather_vec(sm + c.m.stage, xb + XB_Y1, VEC / 4, c.tid);
+            __syncthreads();
+            if (w < 4) {
+                float acc[4][BT];
+                zero_acc(acc);
+                item_fma(sm + c.m.w + W_M4 + w * ITEM, sm + c.m.stage, w * 128, lane, acc);
+                sm[c.m.part + w * 32 + lane] = reduce_scatter32(acc, lane);
+            } else if (t + 1 < S) cond_items(c, w);
+            __syncthreads();
+            const float *part = sm + c.m.part;
+            const float *sv = small(c);
+            if (w == 0) {
+                const int u = lane >> 3;
+                float y = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + pg[PG_P4 + lane] + sv[SV_B4 + u];
+                y = fmaxf(y, 0.f);
+                publish_line(xb + XB_Y2, c.cta, lane, y);
+                raise_flag(flag_base(c, g, 3) + c.cta, epoch, lane);
+            }
+            __syncwarp();
+            if (t + 1 < S) {
+                if (w == 0) pg[PG_P4 + lane] = part[(4 + 11) * 32 + lane];
+                else if (w != 8) cond_finalize(c, g, w);
+            }
+        }
+        // ================= S5: output projection =================================================
+        if (c.cta < p.nprod5) {
+            for (int g = 0; g < G; ++g) {
+                float *xb = xb_base(c, g);
+                if (!cta_wait(c, g, 3, NCTA, epoch)) return;
+                gather_vec(sm + c.m.stage, xb + XB_Y2, VEC / 4, c.tid);
+                __syncthreads();
+                if (w < p.rows5) {
+                    float acc[4][BT];
+                    zero_acc(acc);
+                    item_fma(sm + c.m.w + W_M5 + w * ITEM, sm + c.m.stage, (w & 3) * 128, lane, acc);
+                    sm[c.m.part + w * 32 + lane] = reduce_scatter32(acc, lane);
+                }
+                __syncthreads();
+                if (w * 4 < p.rows5) {
+                    const float *part = sm + c.m.part + w * 128;
+                    const float *sv = small(c);
+                    const float v = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + sv[SV_B5 + w * 4 + (lane >> 3)];
+                    const int k = p.rows5 * c.cta + w * 4 + (lane >> 3);
+                    st_cg(xb + XB_LG + xidx(k, lane & 7), v);
+                }
+                if (p.rows5 > 4) __syncthreads();
+                if (w == 0) raise_flag(flag_base(c, g, 4) + c.cta, epoch, lane);
+            }
+        }
+    }
+}
+
+// Exchange microbenchmark: the same publish / poll / gather sequence on an empty kernel.
+extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe_kernel(const KParams prm)
+{
+    extern __shared__ __align__(128) float sm[];
+    Ctx c;
+    c.p = &prm;
+    c.sm = sm;
+    c.m = smem_map(prm.rows5);
+    c.tid = threadIdx.x;
+    c.lane = c.tid & 31;
+    c.warp = c.tid >> 5;
+    c.cta = blockIdx.x;
+    if (c.tid == 0) *reinterpret_cast<int *>(sm + c.m.mbar + 6) = 0;
+    __syncthreads();
+    float *xb = xb_base(c, 0);
+    float acc = 0.f;
+    for (int it = 0; it < prm.probe_iters; ++it) {
+        const int e = it % NEXCH;
+        const unsigned epoch = (unsigned)(it / NEXCH) + 1u;
+        if (c.warp == 0) {
+            publish_line(xb + XB_H1, c.cta, c.lane, acc + (float)it);
+            raise_flag(flag_base(c, 0, e) + c.cta, epoch, c.lane);
+        }
+        if (!cta_wait(c, 0, e, NCTA, epoch)) return;
+        gather_vec(sm + c.m.stage, xb + XB_H1, VEC / 4, c.tid);
+        __syncthreads();
+        acc += sm[c.m.stage + c.tid];
+    }
+    if (acc == 123.456f) prm.status[1] = 1;      // keep the loads alive
+}
+
+}  // namespace wrnn

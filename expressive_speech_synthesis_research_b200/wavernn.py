@@ -1,0 +1,399 @@
+"""Host-side mirror of the reference vocoder's interface for the generation hot path.
+
+`WaveRNN` keeps the reference constructor keywords, sub-module names (=> identical
+state_dict keys, reference checkpoints load unchanged) and the
+`generate(mels, [save_path,] batched, target, overlap, mu_law)` contract of
+WaveRNN/models/fatchord_version.py:89-243, but the autoregressive loop, the fold
+gather and the crossfade/mu-law epilogue run in the sm_100a library behind
+include/wavernn_b200.h.  PyTorch only runs the non-autoregressive conditioning
+network (MelResNet / UpsampleNetwork, fatchord_version.py:10-86) and owns device memory.
+
+There is no CPU path: generate() raises if CUDA or the compiled library is missing.
+"""
+import ctypes
+import os
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+from .wavio import save_wav
+
+
+class _ResidualUnit(nn.Module):
+    """1x1 conv / BN / ReLU / 1x1 conv / BN + skip (reference ResBlock, fatchord_version.py:10-25)."""
+
+    def __init__(self, dims):
+        super().__init__()
+        self.conv1 = nn.Conv1d(dims, dims, kernel_size=1, bias=False)
+        self.conv2 = nn.Conv1d(dims, dims, kernel_size=1, bias=False)
+        self.batch_norm1 = nn.BatchNorm1d(dims)
+        self.batch_norm2 = nn.BatchNorm1d(dims)
+
+    def forward(self, x):
+        y = F.relu(self.batch_norm1(self.conv1(x)))
+        return self.batch_norm2(self.conv2(y)) + x
+
+
+class MelResNet(nn.Module):
+    """Frame-rate aux feature network (fatchord_version.py:28-45)."""
+
+    def __init__(self, res_blocks, in_dims, compute_dims, res_out_dims, pad):
+        super().__init__()
+        self.conv_in = nn.Conv1d(in_dims, compute_dims, kernel_size=2 * pad + 1, bias=False)
+        self.batch_norm = nn.BatchNorm1d(compute_dims)
+        self.layers = nn.ModuleList(_ResidualUnit(compute_dims) for _ in range(res_blocks))
+        self.conv_out = nn.Conv1d(compute_dims, res_out_dims, kernel_size=1)
+
+    def forward(self, x):
+        x = F.relu(self.batch_norm(self.conv_in(x)))
+        for layer in self.layers:
+            x = layer(x)
+        return self.conv_out(x)
+
+
+class _Repeat(nn.Module):
+    """Nearest-neighbour stretch of the time axis (reference Stretch2d(x_scale, 1), :48-58)."""
+
+    def __init__(self, scale):
+        super().__init__()
+        self.scale = scale
+
+    def forward(self, x):
+        return x.repeat_interleave(self.scale, dim=-1)
+
+
+class UpsampleNetwork(nn.Module):
+    """Mel -> sample-rate conditioning (fatchord_version.py:61-86): aux = repeat(resnet(m), hop);
+    mel = three (repeat, box-filter conv) stages cropped by pad*hop on both sides."""
+
+    def __init__(self, feat_dims, upsample_scales, compute_dims, res_blocks, res_out_dims, pad):
+        super().__init__()
+        self.total_scale = int(np.prod(upsample_scales))
+        self.indent = pad * self.total_scale
+        self.resnet = MelResNet(res_blocks, feat_dims, compute_dims, res_out_dims, pad)
+        self.resnet_stretch = _Repeat(self.total_scale)
+        self.up_layers = nn.ModuleList()
+        for s in upsample_scales:
+            conv = nn.Conv2d(1, 1, kernel_size=(1, 2 * s + 1), padding=(0, s), bias=False)
+            conv.weight.data.fill_(1.0 / (2 * s + 1))
+            self.up_layers.append(_Repeat(s))      # index 0, 2, 4 (no parameters)
+            self.up_layers.append(conv)            # index 1, 3, 5 (state_dict keys up_layers.{1,3,5}.weight)
+
+    def forward(self, m):
+        aux = self.resnet_stretch(self.resnet(m))
+        m = m.unsqueeze(1)
+        for layer in self.up_layers:
+            m = layer(m)
+        m = m.squeeze(1)[:, :, self.indent:-self.indent]
+        return m.transpose(1, 2), aux.transpose(1, 2)
+
+
+class _Engine:
+    """Owns one wrnn_handle (include/wavernn_b200.h) on one CUDA device."""
+
+    def __init__(self, cfg: _lib.Config, device_index: int):
+        self.lib = _lib.lib()
+        self.handle = _lib.vp()
+        self.cfg = cfg
+        self.device_index = device_index
+        _lib.check(self.lib.wrnn_create(ctypes.byref(cfg), device_index, ctypes.byref(self.handle)))
+        self.weights_tag = None
+
+    def load(self, state, tag):
+        keep, w = [], _lib.Weights()
+        for field, key in zip(_lib.Weights.FIELDS, _lib.Weights.KEYS):
+            t = state[key].detach().to("cpu", torch.float32).contiguous()
+            keep.append(t)
+            setattr(w, field, t.data_ptr())
+        _lib.check(self.lib.wrnn_load_weights(self.handle, ctypes.byref(w)))
+        self.weights_tag = tag
+
+    def info(self):
+        out = _lib.Info()
+        _lib.check(self.lib.wrnn_get_info(self.handle, ctypes.byref(out)))
+        return out
+
+    def measure_exchange(self, iters=2000):
+        us = ctypes.c_float()
+        _lib.check(self.lib.wrnn_measure_exchange(self.handle, iters, ctypes.byref(us)))
+        return float(us.value)
+
+    def close(self):
+        if self.handle:
+            self.lib.wrnn_destroy(self.handle)
+            self.handle = _lib.vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class WaveRNN(nn.Module):
+    """Drop-in for models.fatchord_version.WaveRNN on the generation path."""
+
+    def __init__(self, rnn_dims, fc_dims, bits, pad, upsample_factors, feat_dims, compute_dims,
+                 res_out_dims, res_blocks, hop_length, sample_rate, mode='RAW'):
+        super().__init__()
+        self.mode = mode
+        self.pad = pad
+        if mode == 'RAW':
+            self.n_classes = 2 ** bits
+        elif mode == 'MOL':
+            self.n_classes = 30
+        else:
+            raise RuntimeError("Unknown model mode value - %s" % (mode,))   # the reference builds this error but never raises it (:101)
+        self.rnn_dims = rnn_dims
+        self.aux_dims = res_out_dims // 4
+        self.hop_length = hop_length
+        self.sample_rate = sample_rate
+
+        self.upsample = UpsampleNetwork(feat_dims, upsample_factors, compute_dims, res_blocks, res_out_dims, pad)
+        self.I = nn.Linear(feat_dims + self.aux_dims + 1, rnn_dims)
+        self.rnn1 = nn.GRU(rnn_dims, rnn_dims, batch_first=True)
+        self.rnn2 = nn.GRU(rnn_dims + self.aux_dims, rnn_dims, batch_first=True)
+        self.fc1 = nn.Linear(rnn_dims + self.aux_dims, fc_dims)
+        self.fc2 = nn.Linear(fc_dims + self.aux_dims, fc_dims)
+        self.fc3 = nn.Linear(fc_dims, self.n_classes)
+        self.step = nn.Parameter(torch.zeros(1).long(), requires_grad=False)
+
+        self._feat_dims = feat_dims
+        self._fc_dims = fc_dims
+        self._engines = {}
+        self.precision = "fp32"
+        self.last_stats = {}
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _weights_tag(self):
+        sd = self.state_dict()
+        return tuple((sd[k].data_ptr(), sd[k]._version) for k in _lib.Weights.KEYS)
+
+    def _engine(self, device: torch.device) -> _Engine:
+        if device.type != "cuda":
+            raise RuntimeError("WaveRNN.generate runs on a CUDA sm_100 device only (no CPU path); got %s" % device)
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        eng = self._engines.get(idx)
+        if eng is None:
+            cfg = _lib.Config(self.rnn_dims, self._fc_dims, self._feat_dims, self.aux_dims, self.n_classes,
+                              _lib.MODE[self.mode], _lib.PRECISION[self.precision])
+            eng = self._engines[idx] = _Engine(cfg, idx)
+        tag = self._weights_tag()
+        if eng.weights_tag != tag:
+            eng.load(self.state_dict(), tag)
+        return eng
+
+    def _device(self):
+        p = self.I.weight
+        if p.is_cuda:
+            return p.device
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA is not available: the B200 WaveRNN path has no CPU fallback")
+        return torch.device("cuda", torch.cuda.current_device())
+
+    # ------------------------------------------------------------------ conditioning (PyTorch)
+    def conditioning(self, mels):
+        """generate() prologue, fatchord_version.py:162-165: (1, feat, T) -> (L, feat), (L, 4*aux)."""
+        m = F.pad(mels, (self.pad, self.pad))                       # pad_tensor(side='both'), :260-270
+        m, aux = self.upsample(m)
+        return m[0].contiguous(), aux[0].contiguous()
+
+    # ------------------------------------------------------------------ the hot path
+    def generate(self, mels, *args, uniforms=None, seed=None, forced_x=None, return_logits=False,
+                 return_samples=False, **kwargs):
+        """generate(mels, batched, target, overlap, mu_law)            -- this repo (fatchord_version.py:150)
+           generate(mels, save_path, batched, target, overlap, mu_law) -- upstream form, gen_wavernn.py:34,51
+
+        Returns the waveform as float64 numpy of length (T-1)*hop_length.  Extra keyword-only
+        arguments: `uniforms` (pre-drawn U[0,1): [S,B] RAW / [S,B,11] MOL), `seed` (in-kernel
+        Philox when no uniforms are given), `forced_x` [S,B] + `return_logits` (teacher forcing),
+        `return_samples` (also return the per-fold samples / labels).
+        """
+        names = ("batched", "target", "overlap", "mu_law")
+        save_path = kwargs.pop("save_path", None)
+        args = list(args)
+        if args and (args[0] is None or isinstance(args[0], (str, os.PathLike))):
+            save_path = args.pop(0)
+        if len(args) > 4:
+            raise TypeError("generate() takes at most 6 positional arguments")
+        call = dict(zip(names, args))
+        for k in names:
+            if k in kwargs:
+                if k in call:
+                    raise TypeError("generate() got multiple values for argument '%s'" % k)
+                call[k] = kwargs.pop(k)
+        if kwargs:
+            raise TypeError("generate() got unexpected keyword arguments %s" % sorted(kwargs))
+        missing = [k for k in names if k not in call]
+        if missing:
+            raise TypeError("generate() missing required arguments: %s" % ", ".join(missing))
+        batched, target, overlap, mu_law = (call[k] for k in names)
+
+        mu_law = mu_law if self.mode == 'RAW' else False             # :152
+        self.eval()                                                   # :154
+        t_start = time.perf_counter()
+        try:
+            with torch.no_grad():
+                device = self._device()
+                eng = self._engine(device)
+                with torch.cuda.device(device):
+                    out = self._generate_on_device(eng, device, mels, bool(batched), int(target), int(overlap),
+                                                   bool(mu_law), uniforms, seed, forced_x, return_logits)
+        finally:
+            self.train()                                              # :241 (regardless of the prior mode)
+        wav_dev, extras = out
+        wav = wav_dev.cpu().numpy()                                   # D2H, the reference's :223
+        self.last_stats["wall_s"] = time.perf_counter() - t_start
+        if save_path is not None:
+            save_wav(wav, save_path, self.sample_rate)                # upstream :239
+        if return_logits or return_samples:
+            return wav, extras
+        return wav
+
+    def _generate_on_device(self, eng, device, mels, batched, target, overlap, mu_law, uniforms, seed,
+                            forced_x, return_logits):
+        if mels.dim() != 3 or mels.size(0) != 1:
+            raise RuntimeError("mels must have shape (1, feat_dims, T), got %s" % (tuple(mels.shape),))
+        mels = mels.to(device=device, dtype=torch.float32)            # H2D, :162
+        if self.upsample.resnet.conv_in.weight.device != device:
+            self.to(device)
+        T = mels.size(-1)
+        wave_len = (T - 1) * self.hop_length                          # :163
+        tail = 20 * self.hop_length
+        if wave_len < tail:
+            raise ValueError("operands could not be broadcast together: wave_len %d < 20*hop_length %d "
+                             "(the reference needs T >= 21 frames, fatchord_version.py:235-237)" % (wave_len, tail))
+        m_up, aux = self.conditioning(mels)                           # :164-165
+        L = m_up.size(0)
+        if batched:
+            B, _ = _lib.fold_index(L, target, overlap)                # :298-309
+            if B <= 0:
+                raise RuntimeError("fold_with_overlap yields no folds: total_len %d <= overlap %d" % (L, overlap))
+            S = target + 2 * overlap
+            starts = np.arange(B, dtype=np.int64) * (target + overlap)   # :315
+        else:
+            B, S = 1, L
+            starts = np.zeros(1, dtype=np.int64)
+        limits = np.full(B, L, dtype=np.int64)
+        res = self._run_folds(eng, device, m_up, aux, starts, limits, S, uniforms, seed, forced_x, return_logits)
+        wav = torch.empty(wave_len, dtype=torch.float64, device=device)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        _lib.check(eng.lib.wrnn_xfade_unfold(res["samples"].data_ptr(), B, S, int(batched), overlap if batched else 0,
+                                             self.n_classes if mu_law else 0, wave_len, tail, wav.data_ptr(),
+                                             ctypes.c_void_p(stream)))
+        self.last_stats.update(folds=B, steps=S, wave_len=wave_len, kernel_ms=eng.info().last_kernel_ms)
+        return wav, res
+
+    def _run_folds(self, eng, device, m_up, aux, starts, limits, S, uniforms, seed, forced_x, return_logits):
+        """wrnn_generate_folds over conditioning rows; starts/limits are host int64 arrays."""
+        B = len(starts)
+        n_u = 1 if self.mode == 'RAW' else self.n_classes // 3 + 1
+
+        def dev(t, shape, what):
+            if t is None:
+                return None
+            t = torch.as_tensor(t).to(device=device, dtype=torch.float32).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError("%s must have shape %s, got %s" % (what, shape, tuple(t.shape)))
+            return t
+
+        u = dev(uniforms, (S, B) if n_u == 1 else (S, B, n_u), "uniforms")
+        fx = dev(forced_x, (S, B), "forced_x")
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())       # follows torch's global RNG like the reference
+        samples = torch.empty(B, S, dtype=torch.float32, device=device)
+        labels = torch.empty(B, S, dtype=torch.int32, device=device)
+        logits = torch.empty(S, B, self.n_classes, dtype=torch.float32, device=device) if return_logits else None
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        limits = np.ascontiguousarray(limits, dtype=np.int64)
+        stream = torch.cuda.current_stream(device).cuda_stream
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        _lib.check(eng.lib.wrnn_generate_folds(
+            eng.handle, ptr(m_up), ptr(aux), m_up.size(0),
+            starts.ctypes.data_as(ctypes.c_void_p), limits.ctypes.data_as(ctypes.c_void_p), B, S,
+            ptr(u), ctypes.c_uint64(seed), ptr(fx), ptr(logits), ptr(samples), ptr(labels),
+            ctypes.c_void_p(stream)))
+        return dict(samples=samples, labels=labels, logits=logits)
+
+    def generate_many(self, mel_list, target, overlap, mu_law, uniforms=None, seed=None):
+        """Batched generation of several utterances with their folds POOLED into one launch
+        sequence: the reference's callers loop one sentence at a time
+        (synthesize_sentences.py:63-73) and only ever see B = folds of one utterance.
+        Returns a list of float64 waveforms, each equal to generate(mel, True, target, overlap, mu_law)
+        given the matching slice of `uniforms` ([S, total_folds(,11)], utterance-major fold order)."""
+        mu_law = mu_law if self.mode == 'RAW' else False
+        self.eval()
+        try:
+            with torch.no_grad():
+                device = self._device()
+                eng = self._engine(device)
+                with torch.cuda.device(device):
+                    if self.upsample.resnet.conv_in.weight.device != device:
+                        self.to(device)
+                    conds, starts, limits, meta, base = [], [], [], [], 0
+                    S = target + 2 * overlap
+                    for mel in mel_list:
+                        mel = mel.to(device=device, dtype=torch.float32)
+                        wave_len = (mel.size(-1) - 1) * self.hop_length
+                        if wave_len < 20 * self.hop_length:
+                            raise ValueError("utterance shorter than 21 frames")
+                        m_up, aux = self.conditioning(mel)
+                        L = m_up.size(0)
+                        B, _ = _lib.fold_index(L, target, overlap)
+                        if B <= 0:
+                            raise RuntimeError("utterance yields no folds")
+                        starts.append(base + np.arange(B, dtype=np.int64) * (target + overlap))
+                        limits.append(np.full(B, base + L, dtype=np.int64))
+                        meta.append((B, wave_len))
+                        conds.append((m_up, aux))
+                        base += L
+                    m_all = torch.cat([c[0] for c in conds]).contiguous()
+                    a_all = torch.cat([c[1] for c in conds]).contiguous()
+                    res = self._run_folds(eng, device, m_all, a_all, np.concatenate(starts), np.concatenate(limits), S,
+                                          uniforms, seed, None, False)
+                    stream = torch.cuda.current_stream(device).cuda_stream
+                    outs, b0 = [], 0
+                    for B, wave_len in meta:
+                        wav = torch.empty(wave_len, dtype=torch.float64, device=device)
+                        _lib.check(eng.lib.wrnn_xfade_unfold(res["samples"][b0:b0 + B].data_ptr(), B, S, 1, overlap,
+                                                             self.n_classes if mu_law else 0, wave_len,
+                                                             20 * self.hop_length, wav.data_ptr(), ctypes.c_void_p(stream)))
+                        outs.append(wav)
+                        b0 += B
+                    self.last_stats.update(folds=b0, steps=S, kernel_ms=eng.info().last_kernel_ms)
+                    return [w.cpu().numpy() for w in outs]
+        finally:
+            self.train()
+
+    # ------------------------------------------------------------------ reference housekeeping API
+    def get_step(self):
+        return self.step.data.item()
+
+    def checkpoint(self, path):
+        self.save('%s/checkpoint_%dk_steps.pyt' % (path, self.get_step() // 1000))
+
+    def log(self, path, msg):
+        with open(path, 'a') as f:
+            print(msg, file=f)
+
+    def restore(self, path):
+        if not os.path.exists(path):
+            self.save(path)
+        else:
+            self.load(path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path, map_location="cpu"), strict=False)
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def num_params(self, print_out=True):
+        n = sum(int(np.prod(p.size())) for p in self.parameters() if p.requires_grad) / 1_000_000
+        if print_out:
+            print('Trainable Parameters: %.3fM' % n)
+        return n

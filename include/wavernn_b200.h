@@ -1,0 +1,155 @@
+/*
+ * wavernn_b200.h -- C ABI of the B200-native WaveRNN batched-generation hot path.
+ *
+ * The reference (sankar-mukherjee/Expressive-Speech-Synthesis-Research) has no FFI for this
+ * path: the boundary is the Python method WaveRNN.generate (WaveRNN/models/fatchord_version.py:150).
+ * Each entry point below replaces the part of that method named beside it; the Python host
+ * mirror (expressive_speech_synthesis_research_b200/wavernn.py) binds them with ctypes and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: plain C types, raw pointers and sizes only (no torch types).  Every function
+ * returns 0 on success or a negative wrnn_status; wrnn_last_error() gives the thread-local
+ * message.  Pointers marked [dev] are CUDA device pointers borrowed for the duration of the
+ * call; [host] are host pointers.  `stream` is a cudaStream_t passed as void* (NULL = default
+ * stream).  Work is enqueued asynchronously on `stream` unless stated otherwise.  One handle
+ * per device; a handle is NOT re-entrant (the persistent kernel occupies 128 SMs).
+ * There is no CPU fallback: every compute entry point fails with WRNN_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef WAVERNN_B200_H
+#define WAVERNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WRNN_ABI_VERSION 1
+
+typedef enum {
+    WRNN_OK = 0,
+    WRNN_ERR_INVALID = -1,     /* bad argument / unsupported configuration */
+    WRNN_ERR_CUDA = -2,        /* CUDA runtime error (message has the cudaError string) */
+    WRNN_ERR_STATE = -3,       /* e.g. generate before load_weights */
+    WRNN_ERR_TIMEOUT = -4      /* in-kernel watchdog: a grid-level exchange never completed */
+} wrnn_status;
+
+enum { WRNN_MODE_RAW = 0, WRNN_MODE_MOL = 1 };
+enum { WRNN_PREC_FP32 = 0, WRNN_PREC_BF16 = 1 };
+
+/* Model geometry: WaveRNN.__init__, fatchord_version.py:90-114. */
+typedef struct {
+    int32_t rnn_dims;    /* 512 */
+    int32_t fc_dims;     /* 512 */
+    int32_t feat_dims;   /* 80  */
+    int32_t aux_dims;    /* res_out_dims / 4 = 32 (fatchord_version.py:104) */
+    int32_t n_classes;   /* 2**bits (RAW) or 30 (MOL) (fatchord_version.py:96-99) */
+    int32_t mode;        /* WRNN_MODE_* */
+    int32_t precision;   /* WRNN_PREC_*: storage of the resident weights / exchanged activations */
+} wrnn_config;
+
+/* The sixteen state_dict tensors on the step path, torch [out, in] row-major fp32, HOST memory
+ * (keys I.*, rnn1.*_l0, rnn2.*_l0, fc1.*, fc2.*, fc3.*). */
+typedef struct {
+    const float *I_w, *I_b;
+    const float *r1_wih, *r1_whh, *r1_bih, *r1_bhh;
+    const float *r2_wih, *r2_whh, *r2_bih, *r2_bhh;
+    const float *fc1_w, *fc1_b, *fc2_w, *fc2_b, *fc3_w, *fc3_b;
+} wrnn_weights;
+
+typedef struct wrnn_handle wrnn_handle;
+
+/* ABI version of the loaded library (== WRNN_ABI_VERSION of the header it was built from). */
+int32_t wrnn_abi_version(void);
+
+/* Thread-local message of the last failing call on this thread ("" if none). */
+const char *wrnn_last_error(void);
+
+/* Create / destroy the per-device engine (allocates exchange buffers, flags, workspace).
+ * Replaces: module construction + .cuda() placement, synthesizer_wavernn.py:17-28. */
+int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_handle **out);
+void wrnn_destroy(wrnn_handle *h);
+
+/* Repack the reference's weights into per-SM shared-memory images and upload them
+ * (synchronous).  Replaces: restore()/load(), fatchord_version.py:396-405, and get_gru_cell,
+ * :252-258.  May be called again to swap checkpoints. */
+int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w /* [host] */);
+
+/* Host-only view of the repack (no GPU needed): the per-CTA shared-memory weight images that
+ * wrnn_load_weights uploads, [128][wrnn_packed_floats/128] floats.  Used by the CPU tests to
+ * check the algebraic folding of I / conditioning terms against the oracle. */
+int64_t wrnn_packed_floats(const wrnn_config *cfg);
+int32_t wrnn_pack_weights_host(const wrnn_config *cfg, const wrnn_weights *w /* [host] */,
+                               float *out /* [host] */, int64_t out_floats);
+
+/* fold_with_overlap index arithmetic, fatchord_version.py:298-309 (pure host integer code).
+ * num_folds may be 0 (total_len <= overlap).  padded_len is the reference's padded length. */
+int32_t wrnn_fold_index(int64_t total_len, int64_t target, int64_t overlap,
+                        int64_t *num_folds, int64_t *padded_len);
+
+/*
+ * The hot loop: fatchord_version.py:171-222 for `num_folds` independent folds of `steps`
+ * samples each, reading the UNFOLDED conditioning by index (fold_with_overlap's gather,
+ * :311-319, is fused: fold b reads rows fold_start[b] + s; rows >= fold_limit[b] are the
+ * zero padding of :306-309).  Folds of several utterances may be pooled in one call.
+ *
+ *   mels  [dev] float32 [cond_rows, feat_dims]      upsampled mel  (UpsampleNetwork, :79-86)
+ *   aux   [dev] float32 [cond_rows, 4*aux_dims]     upsampled aux
+ *   fold_start, fold_limit [host] int64 [num_folds] first row / one-past-last valid row
+ *   uniforms [dev] float32: RAW [steps, num_folds], MOL [steps, num_folds, n_classes/3+1];
+ *            NULL => drawn in-kernel from Philox4x32-10(seed)
+ *   forced_x [dev] float32 [steps, num_folds] or NULL: teacher forcing, value fed back after
+ *            step s instead of the sample (WaveRNN.forward semantics, :119-148)
+ *   logits_out  [dev] float32 [steps, num_folds, n_classes] or NULL
+ *   samples_out [dev] float32 [num_folds, steps]    (the tensor of :222, before .cpu())
+ *   labels_out  [dev] int32   [num_folds, steps] or NULL   RAW: class index; MOL: mixture index
+ */
+int32_t wrnn_generate_folds(wrnn_handle *h,
+                            const float *mels, const float *aux, int64_t cond_rows,
+                            const int64_t *fold_start, const int64_t *fold_limit,
+                            int32_t num_folds, int32_t steps,
+                            const float *uniforms, uint64_t seed,
+                            const float *forced_x, float *logits_out,
+                            float *samples_out, int32_t *labels_out, void *stream);
+
+/*
+ * generate() epilogue on the device, fatchord_version.py:222-237:
+ * widen to float64, xfade_and_unfold (:321-383, bit-exact: mul and add kept separate),
+ * optional decode_mu_law (utility/dsp.py:100-105; pow within 2 ulp), trim to wave_len,
+ * linear tail fade over the last tail_fade samples (:235-237).
+ *   samples [dev] float32 [num_folds, steps];  batched=0: num_folds must be 1, no crossfade
+ *   mu_law_classes: 0 = off, else n_classes
+ *   out [dev] float64 [wave_len]
+ * Fails with WRNN_ERR_INVALID where the reference raises (overlap <= 0 when batched,
+ * tail_fade > wave_len, wave_len beyond the unfolded length).
+ */
+int32_t wrnn_xfade_unfold(const float *samples, int32_t num_folds, int32_t steps,
+                          int32_t batched, int32_t overlap, int32_t mu_law_classes,
+                          int64_t wave_len, int32_t tail_fade, double *out, void *stream);
+
+/* Introspection used by bench.py / tests. */
+typedef struct {
+    int32_t ctas;                /* CTAs of the persistent kernel (one per SM) */
+    int32_t threads;             /* threads per CTA */
+    int32_t smem_bytes;          /* dynamic shared memory per CTA */
+    int32_t folds_per_group;     /* folds advanced together through one exchange */
+    int32_t max_folds_per_launch;
+    int32_t exchanges_per_step;  /* grid-level exchanges on the critical path of one step */
+    int32_t sm_count;
+    int64_t launches;            /* persistent-kernel launches since create */
+    int64_t epilogue_launches;
+    int32_t last_kernel_status;  /* 0 ok, else WRNN_ERR_TIMEOUT */
+    float   last_kernel_ms;      /* device time of the last generate_folds (CUDA events) */
+} wrnn_info;
+int32_t wrnn_get_info(wrnn_handle *h, wrnn_info *out);
+
+/* Microbenchmark of the grid-level exchange used by the step loop (publish 128 B + flag,
+ * poll 128 flags, gather 16 KiB), `iters` times on an otherwise empty persistent kernel.
+ * Writes the mean device time per exchange in microseconds.  Synchronous. */
+int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *usec_per_exchange);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAVERNN_B200_H */
