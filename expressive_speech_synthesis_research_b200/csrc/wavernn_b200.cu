@@ -37,8 +37,8 @@ struct wrnn_handle {
     int rows5 = 4, nprod5 = 128, cpad = 512, n_u = 1;
     int smem_bytes = 0;
     bool loaded = false;
-    float *wimg = nullptr, *xb = nullptr;
-    unsigned *flags = nullptr;
+    float *wimg = nullptr;
+    unsigned long long *xb = nullptr;   // LL exchange buffers
     int *status = nullptr;
     long long *fold_dev = nullptr;   // [2][fold_cap]
     int fold_cap = 0;
@@ -46,8 +46,8 @@ struct wrnn_handle {
     int64_t launches = 0, epilogue_launches = 0;
     int last_status = 0;
     float last_ms = 0.f;
-    double *fade_dev = nullptr;      // cached epilogue tables [fade_in | fade_out | tail]
-    int fade_overlap = -1, fade_tail = -1;
+    long long *prof_dev = nullptr;   // [NCTA][PROF_SLOTS], allocated by wrnn_set_profiling
+    bool profiling = false;
 };
 
 extern "C" int32_t wrnn_abi_version(void) { return WRNN_ABI_VERSION; }
@@ -146,9 +146,7 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
         return fail(WRNN_ERR_CUDA, "persistent kernel does not fit on an SM");
     }
     H_TRY(cudaMalloc(&h->wimg, (size_t)NCTA * w_total(rows5) * sizeof(float)));
-    H_TRY(cudaMalloc(&h->xb, (size_t)MAXG * xb_group(h->cpad) * sizeof(float)));
-    H_TRY(cudaMemset(h->xb, 0, (size_t)MAXG * xb_group(h->cpad) * sizeof(float)));
-    H_TRY(cudaMalloc(&h->flags, (size_t)MAXG * NEXCH * NCTA * sizeof(unsigned)));
+    H_TRY(cudaMalloc(&h->xb, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long)));
     H_TRY(cudaMalloc(&h->status, 4 * sizeof(int)));
     H_TRY(cudaEventCreate(&h->ev0));
     H_TRY(cudaEventCreate(&h->ev1));
@@ -163,10 +161,9 @@ extern "C" void wrnn_destroy(wrnn_handle *h)
     cudaSetDevice(h->device);
     cudaFree(h->wimg);
     cudaFree(h->xb);
-    cudaFree(h->flags);
     cudaFree(h->status);
     cudaFree(h->fold_dev);
-    cudaFree(h->fade_dev);
+    cudaFree(h->prof_dev);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -332,7 +329,8 @@ extern "C" int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w)
 static int32_t launch_chunk(wrnn_handle *h, KParams &p, cudaStream_t st, bool probe)
 {
     void *args[] = {&p};
-    CUDA_TRY(cudaMemsetAsync(h->flags, 0, (size_t)MAXG * NEXCH * NCTA * sizeof(unsigned), st));
+    // epochs restart at 1 every launch: clear stale {value, epoch} pairs of the previous one
+    CUDA_TRY(cudaMemsetAsync(h->xb, 0, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     CUDA_TRY(cudaLaunchCooperativeKernel(probe ? (const void *)wavernn_exchange_probe_kernel : (const void *)wavernn_persistent_kernel,
@@ -355,7 +353,6 @@ static void fill_common(wrnn_handle *h, KParams &p)
     memset(&p, 0, sizeof p);
     p.wimg = h->wimg;
     p.xb = h->xb;
-    p.flags = h->flags;
     p.status = h->status;
     p.C = h->cfg.n_classes;
     p.mode = h->cfg.mode;
@@ -409,6 +406,7 @@ extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const 
         p.samples_out = samples_out;
         p.labels_out = labels_out;
         p.seed = seed;
+        p.prof = h->profiling ? h->prof_dev : nullptr;
         p.B = num_folds;
         p.S = steps;
         p.G = (nb + BT - 1) / BT;
@@ -440,6 +438,25 @@ extern "C" int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *u
     rc = launch_chunk(h, p, nullptr, true);
     if (rc) return rc;
     *usec_per_exchange = h->last_ms * 1000.f / (float)iters;
+    return WRNN_OK;
+}
+
+extern "C" int32_t wrnn_set_profiling(wrnn_handle *h, int32_t enable)
+{
+    if (!h) return fail(WRNN_ERR_INVALID, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (enable && !h->prof_dev) CUDA_TRY(cudaMalloc(&h->prof_dev, (size_t)NCTA * PROF_SLOTS * sizeof(long long)));
+    h->profiling = enable != 0;
+    return WRNN_OK;
+}
+
+extern "C" int32_t wrnn_get_stage_cycles(wrnn_handle *h, int64_t *out, int32_t n)
+{
+    if (!h || !out) return fail(WRNN_ERR_INVALID, "null argument");
+    if (!h->prof_dev) return fail(WRNN_ERR_STATE, "profiling was never enabled");
+    if (n != NCTA * PROF_SLOTS) return fail(WRNN_ERR_INVALID, "n must be %d", NCTA * PROF_SLOTS);
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpy(out, h->prof_dev, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
     return WRNN_OK;
 }
 

@@ -4,9 +4,12 @@
 //  * 128 CTAs (one per SM, cooperative launch), each owns 4 of the 512 hidden units of every
 //    layer; its rows of every weight matrix stay resident in shared memory for all steps.
 //  * Folds advance in groups of 8.  A group goes through 5 grid-level exchanges per step
-//    (h1 | h2,s | y1 | y2 | logits): a CTA publishes one 128-byte line + a flag, polls the
-//    128 flags, gathers the 16 KiB vector from L2.  Groups are interleaved in a static order
-//    so one group's exchange latency hides behind the other groups' mat-vecs.
+//    (h1 | h2 | y1 | y2 | logits).  The exchange is flag-free ("LL" protocol): every value
+//    travels as an 8-byte {fp32 value, step epoch} pair written with one store; a consumer
+//    polls the pairs it needs until their epoch matches -- one L2 round trip, no fences, no
+//    contended flag lines (measured 1.4 us per 128-CTA all-gather vs 2.5-6.6 us with
+//    release/acquire flags; profiles/r01_exchange_microbench.md).  Groups are interleaved in
+//    a static order so one group's exchange latency hides behind the others' mat-vecs.
 //  * The input layer I and every conditioning term are folded algebraically into the
 //    downstream layers at load time (host, fp64), so the recurrence only multiplies
 //    h1, h2, s=h1+h2, y1, y2; conditioning projections for step t+1 are computed during
@@ -26,7 +29,7 @@ constexpr int BT = 8;             // folds per group (one 32-byte row of an exch
 constexpr int NTHREADS = 512;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAXG = 8;           // groups per launch -> 64 folds
-constexpr int VEC = HID * BT;     // floats of one exchanged vector (16 KiB)
+constexpr int VEC = HID * BT;     // values of one exchanged vector (16 KiB in smem, 32 KiB of LL pairs in L2)
 constexpr int ITEM = 4 * 32 * 4;  // floats of one weight item image: 4 rows x 128 k
 constexpr int NEXCH = 5;
 constexpr int CONDK = 256;        // padded conditioning length (80 mel + 4*32 aux = 208)
@@ -34,7 +37,7 @@ constexpr int COND_ITEMS = 12;
 
 // ---- per-CTA weight image (floats) --------------------------------------------------------
 constexpr int W_M2 = 0;                       // 24 rows: Wih2x gates (12) | Whh1 gates (12), x H1
-constexpr int W_M3 = W_M2 + 24 * HID;         // 16 rows: Wfc1x (4) x S | Whh2 gates (12) x H2
+constexpr int W_M3 = W_M2 + 24 * HID;         // 16 rows: Wfc1x (4) x H1 (S2) and x H2 (S3) | Whh2 gates (12) x H2
 constexpr int W_M4 = W_M3 + 16 * HID;         // 4 rows: Wfc2x x Y1
 constexpr int W_M5 = W_M4 + 4 * HID;          // rows5 rows: Wfc3 x Y2
 __host__ __device__ constexpr int w_mc(int rows5) { return W_M5 + rows5 * HID; }           // 12 cond items
@@ -46,23 +49,24 @@ __host__ __device__ constexpr int w_total(int rows5) { return w_small(rows5) + S
 
 // ---- per-group private state (floats) -----------------------------------------------------
 constexpr int PG_GH1 = 0, PG_GH2 = 96, PG_P1 = 192, PG_P2 = 288, PG_P3 = 384, PG_P4 = 416,
-              PG_H1 = 448, PG_H2 = 480, PG_X = 512, PG_U = 520, PG_FX = 608, PG_SIZE = 640;
+              PG_H1 = 448, PG_H2 = 480, PG_X = 512, PG_U = 520, PG_FX = 608, PG_F1 = 616, PG_SIZE = 656;
 
 // ---- shared memory map (floats) -----------------------------------------------------------
 struct SmemMap {
-    int w, stage, cx, cstage, part, priv, samp, mbar, total;
+    int w, stage, cx, cstage, part, priv, samp, tab, mbar, total;
 };
 __host__ __device__ inline SmemMap smem_map(int rows5)
 {
     SmemMap m;
     m.w = 0;
     m.stage = m.w + w_total(rows5);
-    m.cx = m.stage + 2 * VEC;
+    m.cx = m.stage + (rows5 > 4 ? 2 : 1) * VEC;     // 1024-class logits need 8192 floats
     m.cstage = m.cx + CONDK * BT;
     m.part = m.cstage + 2 * BT * 208;
     m.priv = m.part + NWARPS * 32;
     m.samp = m.priv + MAXG * PG_SIZE;
-    m.mbar = m.samp + 1024;
+    m.tab = m.samp + 1024;                          // work table: 4 item stages x 16 warps x int4
+    m.mbar = m.tab + 4 * NWARPS * 4;
     m.total = m.mbar + 8;
     return m;
 }
@@ -74,41 +78,31 @@ struct KParams {
     const float *uniforms, *forced_x;
     float *logits_out, *samples_out;
     int *labels_out;
-    float *xb;                         // [G][xb_group]  exchange buffers
-    unsigned *flags;                   // [G][NEXCH][NCTA]
+    unsigned long long *xb;            // [G][xb_group] exchange buffers of {value, epoch} pairs
     int *status;
     unsigned long long seed;
     int B, S, G, C, mode, rows5, nprod5, n_u;   // n_u: uniforms per fold-step (1 RAW, 11 MOL)
     int feat, auxw;                    // 80, 128
     int group_fold0[MAXG], group_nf[MAXG];
     int probe_iters;
+    long long *prof;                   // optional [NCTA][PROF_SLOTS] per-stage cycle counters (clock64, thread 0)
 };
-constexpr int XB_H1 = 0, XB_H2 = VEC, XB_S = 2 * VEC, XB_Y1 = 3 * VEC, XB_Y2 = 4 * VEC, XB_LG = 5 * VEC;
-__host__ __device__ constexpr int xb_group(int cpad) { return 5 * VEC + cpad * BT; }
+constexpr int PROF_SLOTS = 24;
+constexpr int XB_H1 = 0, XB_H2 = VEC, XB_Y1 = 2 * VEC, XB_Y2 = 3 * VEC, XB_LG = 4 * VEC;     // in pairs
+__host__ __device__ constexpr int xb_group(int cpad) { return 4 * VEC + cpad * BT; }
 
 // ============================================================================================
 // device helpers
 // ============================================================================================
-__device__ __forceinline__ float4 ldg_cg4(const float *p)
-{
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint4 ld_flags4(const unsigned *p)
+__device__ __forceinline__ uint4 ld_pairs2(const unsigned long long *p)      // two {value, epoch} pairs, L2 (never L1)
 {
     uint4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void st_flag(unsigned *p, unsigned v)
+__device__ __forceinline__ void st_pair(unsigned long long *p, float v, unsigned epoch)   // one 8-byte store
 {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void st_cg(float *p, float v)
-{
-    asm volatile("st.global.cg.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -154,44 +148,46 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
 }
 __device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
-// Poll `nprod` (<=128) producer flags until all reach `epoch`.  Warp 0 only.  false = watchdog.
-__device__ __forceinline__ bool wait_flags(const unsigned *flags, int nprod, unsigned epoch, int lane)
-{
-    const bool mine = lane * 4 < nprod;
-    for (int spin = 0; spin < (1 << 22); ++spin) {
-        bool ok = true;
-        if (mine) {
-            uint4 v = ld_flags4(flags + lane * 4);
-            ok = (v.x >= epoch) & (v.y >= epoch) & (v.z >= epoch) & (v.w >= epoch);
-        }
-        if (__all_sync(0xffffffffu, ok)) {
-            fence_gpu();
-            return true;
-        }
-    }
-    return false;
-}
+constexpr int POLL_CAP = 1 << 22;    // watchdog: ~1 s of polling
 
-// Gather `n4` float4 from an exchange buffer (L2; never L1) into shared memory.  All threads.
-__device__ __forceinline__ void gather_vec(float *dst, const float *src, int n4, int tid)
+// LL gather of `npairs` (multiple of 2) {value, epoch} pairs from L2 into the swizzled [k][8]
+// shared-memory layout; each thread polls its own 16-byte chunks until both epochs match.
+// Returns false if the watchdog fired (thread-local; the caller makes it CTA-uniform).
+__device__ __forceinline__ bool gather_ll(float *dst, const unsigned long long *src, int npairs, unsigned epoch, int tid)
 {
-    if (n4 == VEC / 4) {
-        float4 a = ldg_cg4(src + 4 * tid);
-        float4 b = ldg_cg4(src + 4 * (tid + NTHREADS));
-        *reinterpret_cast<float4 *>(dst + 4 * tid) = a;
-        *reinterpret_cast<float4 *>(dst + 4 * (tid + NTHREADS)) = b;
+    bool ok = true;
+    if (npairs == VEC) {
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = ld_pairs2(src + 2 * (tid + j * NTHREADS));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = tid + j * NTHREADS;              // chunk: k = i / 4, folds 2*(i%4), +1
+            int spin = 0;
+            while (v[j].y != epoch || v[j].w != epoch) {
+                if (++spin > POLL_CAP) { ok = false; break; }
+                v[j] = ld_pairs2(src + 2 * i);
+            }
+            *reinterpret_cast<float2 *>(dst + xidx(i >> 2, (i & 3) * 2)) = make_float2(__uint_as_float(v[j].x), __uint_as_float(v[j].z));
+        }
     } else {
-        for (int i = tid; i < n4; i += NTHREADS) {
-            float4 a = ldg_cg4(src + 4 * i);
-            *reinterpret_cast<float4 *>(dst + 4 * i) = a;
+        for (int i = tid; i < npairs / 2; i += NTHREADS) {
+            uint4 v = ld_pairs2(src + 2 * i);
+            int spin = 0;
+            while (v.y != epoch || v.w != epoch) {
+                if (++spin > POLL_CAP) { ok = false; break; }
+                v = ld_pairs2(src + 2 * i);
+            }
+            *reinterpret_cast<float2 *>(dst + xidx(i >> 2, (i & 3) * 2)) = make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
         }
     }
+    return ok;
 }
 
 // One work item: acc[4 rows][8 folds] += W[4][128 k] * X[128 k][8 folds].
 // wimg: item image [4][32 lanes] float4, element i of lane l = W[row][kbase + l + 32 i].
-// xs: exchanged vector in shared memory; lane l consumes k = kbase + l + 32 i.
-__device__ __forceinline__ void item_fma(const float *wimg, const float *xs, int kbase, int lane, float (&acc)[4][BT])
+// xs: exchanged vector in shared memory at row kbase (a multiple of 128); lane l consumes k = kbase + l + 32 i.
+__device__ __forceinline__ void item_fma(const float *wimg, const float *xs, int lane, float (&acc)[4][BT])
 {
     float4 w[4];
 #pragma unroll
@@ -199,7 +195,7 @@ __device__ __forceinline__ void item_fma(const float *wimg, const float *xs, int
     const int sw = ((lane >> 2) & 1) * 4;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float *xp = xs + (kbase + lane + 32 * i) * BT;
+        const float *xp = xs + (lane + 32 * i) * BT;
         const float4 lo = *reinterpret_cast<const float4 *>(xp + sw);        // folds 0..3
         const float4 hi = *reinterpret_cast<const float4 *>(xp + (4 - sw));  // folds 4..7
 #pragma unroll
@@ -249,20 +245,11 @@ __device__ __forceinline__ void zero_acc(float (&acc)[4][BT])
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
-// Publish this CTA's 4 x 8 values of one exchanged vector (one 128-byte line) and raise its flag.
-// Warp 0 only; lane = unit*8 + fold.
-__device__ __forceinline__ void publish_line(float *vec, int cta, int lane, float val)
+// Publish this CTA's 4 x 8 values of one exchanged vector: 32 lanes x 8-byte pairs = 256 contiguous
+// bytes.  Warp 0 only; lane = unit*8 + fold.  No fence, no flag: the epoch rides with the value.
+__device__ __forceinline__ void publish_line(unsigned long long *vec, int cta, int lane, float val, unsigned epoch)
 {
-    const int k = UNITS * cta + (lane >> 3);
-    st_cg(vec + xidx(k, lane & 7), val);
-}
-__device__ __forceinline__ void raise_flag(unsigned *flag, unsigned epoch, int lane)
-{
-    __syncwarp();
-    if (lane == 0) {
-        fence_gpu();
-        st_flag(flag, epoch);
-    }
+    st_pair(vec + (UNITS * cta) * BT + lane, val, epoch);
 }
 
 // ============================================================================================
@@ -274,26 +261,33 @@ struct Ctx {
     SmemMap m;
     int tid, lane, warp, cta;
     int cond_visit;      // running count of conditioning visits (selects staging buffer / parity)
+    long long tprev;     // profiling: last timestamp (thread 0)
 };
+// profiling tick: charge the cycles since the previous tick to `slot` (thread 0 of the CTA only)
+__device__ __forceinline__ void tick(Ctx &c, int slot)
+{
+    if (c.p->prof && c.tid == 0) {
+        const long long now = clock64();
+        reinterpret_cast<long long *>(c.sm + c.m.samp + 768)[slot] += now - c.tprev;
+        c.tprev = now;
+    }
+}
 
 __device__ __forceinline__ float *priv(const Ctx &c, int g) { return c.sm + c.m.priv + g * PG_SIZE; }
 __device__ __forceinline__ const float *small(const Ctx &c) { return c.sm + c.m.w + w_small(c.p->rows5); }
-__device__ __forceinline__ unsigned *flag_base(const Ctx &c, int g, int e) { return c.p->flags + ((size_t)g * NEXCH + e) * NCTA; }
-__device__ __forceinline__ float *xb_base(const Ctx &c, int g)
+__device__ __forceinline__ unsigned long long *xb_base(const Ctx &c, int g)
 {
     return c.p->xb + (size_t)g * xb_group(c.p->rows5 * c.p->nprod5);
 }
 
-// Block until the flags of (g, e) reach `epoch`; returns false on watchdog (CTA-uniform).
-__device__ __forceinline__ bool cta_wait(Ctx &c, int g, int e, int nprod, unsigned epoch)
+// LL-gather one exchanged vector of group g into the staging buffer; CTA-uniform result
+// (false = watchdog fired somewhere in this CTA; the kernel then exits and the host reports it).
+__device__ __forceinline__ bool cta_gather(Ctx &c, const unsigned long long *src, int npairs, unsigned epoch)
 {
     int *abort_flag = reinterpret_cast<int *>(c.sm + c.m.mbar + 6);
-    if (c.warp == 0) {
-        bool ok = wait_flags(flag_base(c, g, e), nprod, epoch, c.lane);
-        if (!ok && c.lane == 0) {
-            *abort_flag = 1;
-            atomicExch(c.p->status, -4);
-        }
+    if (!gather_ll(c.sm + c.m.stage, src, npairs, epoch, c.tid)) {
+        *abort_flag = 1;
+        atomicExch(c.p->status, -4);
     }
     __syncthreads();
     return *abort_flag == 0;
@@ -354,17 +348,8 @@ __device__ __forceinline__ void cond_visit(Ctx &c)
     if (c.warp == NWARPS - 1) cond_issue(c, v + 1);
 }
 
-// The 12 conditioning items (warps 4..15) and their finalisation into P1..P4 of group g.
-__device__ __forceinline__ void cond_items(Ctx &c, int w)
-{
-    // item order: 0-2 P1 (chunk A) | 3-8 P2 (rg*2 + chunk) | 9,10 P3 (A,B) | 11 P4 (B)
-    const int it = w - 4;
-    const int chunk = (it < 3) ? 0 : (it < 9) ? ((it - 3) & 1) : (it == 9) ? 0 : 1;
-    float acc[4][BT];
-    zero_acc(acc);
-    item_fma(c.sm + c.m.w + w_mc(c.p->rows5) + it * ITEM, c.sm + c.m.cx, chunk * 128, c.lane, acc);
-    c.sm[c.m.part + w * 32 + c.lane] = reduce_scatter32(acc, c.lane);
-}
+// Finalisation of the 12 conditioning items (work-table slots 4..15 of stage S4) into P1..P4 of group g.
+// item order: 0-2 P1 (chunk A) | 3-8 P2 (rg*2 + chunk) | 9,10 P3 (A,B) | 11 P4 (B)
 __device__ __forceinline__ void cond_finalize(Ctx &c, int g, int w)
 {
     float *pg = priv(c, g);
@@ -405,6 +390,7 @@ __device__ __forceinline__ void prefetch_draws(Ctx &c, int g, int step)
 }
 
 // ---- sampling (all threads): logits of step s are in c.sm[stage]; writes x into priv ---------
+template <int NBI>
 __device__ __forceinline__ void sample_raw(Ctx &c, int g, int s)
 {
     const KParams &p = *c.p;
@@ -413,9 +399,9 @@ __device__ __forceinline__ void sample_raw(Ctx &c, int g, int s)
     float *pg = priv(c, g);
     const int lane = c.lane, f = lane & 7, cs = lane >> 3;
     const int nblk = p.C >> 5;
-    float e[2][8];
+    float e[NBI][8];
 #pragma unroll
-    for (int bi = 0; bi < 2; ++bi) {
+    for (int bi = 0; bi < NBI; ++bi) {
         const int blk = c.warp + bi * NWARPS;
         if (blk < nblk) {
             float v[8], bm = -INFINITY;
@@ -500,7 +486,7 @@ __device__ __forceinline__ void sample_raw(Ctx &c, int g, int s)
         const int own = __float_as_int(sc[512 + f]);
         const float thr_local = sc[520 + f];
 #pragma unroll
-        for (int bi = 0; bi < 2; ++bi) {
+        for (int bi = 0; bi < NBI; ++bi) {
             const int blk = c.warp + bi * NWARPS;
             if (blk < nblk) {                    // warp-uniform
                 float rowbase = 0.f;
@@ -595,6 +581,48 @@ __device__ __forceinline__ void dump_logits(Ctx &c, int g, int s)
     }
 }
 
+// One copy of the mat-vec code serves every stage (the loop body must stay inside the 32 KiB
+// instruction cache: with the items inlined per stage the kernel was instruction-fetch bound,
+// profiles/r01_stage_cycles.md).  Work table entry of (stage, warp): x = weight image offset,
+// y = shared-memory offset of the first consumed row of the input vector, z = number of
+// consecutive 128-k items accumulated into one 4x8 tile (0 = warp idle in this stage).
+__device__ __forceinline__ void run_items(Ctx &c, int stage, bool enable)
+{
+    const int4 wk = reinterpret_cast<const int4 *>(c.sm + c.m.tab)[stage * NWARPS + c.warp];
+    if (wk.z == 0 || !enable) return;
+    float acc[4][BT];
+    zero_acc(acc);
+    for (int it = 0; it < wk.z; ++it) item_fma(c.sm + wk.x + it * ITEM, c.sm + wk.y + it * 128 * BT, c.lane, acc);
+    c.sm[c.m.part + c.warp * 32 + c.lane] = reduce_scatter32(acc, c.lane);
+}
+
+__device__ __forceinline__ void build_work_table(Ctx &c)
+{
+    if (c.tid >= 4 * NWARPS) return;
+    const int stage = c.tid / NWARPS, w = c.tid % NWARPS, rows5 = c.p->rows5;
+    int4 e = make_int4(0, 0, 0, 0);
+    const int W = c.m.w, X = c.m.stage;
+    if (stage == 0) {                                   // S2 (x H1): rg 0-2 Wih2x | 3-5 Whh1 | 6 Wfc1x; two K halves
+        if (w < 14) {
+            const int rg = w % 7, half = w / 7;
+            e = make_int4(W + (rg < 6 ? W_M2 + rg * 4 * ITEM : W_M3) + half * 2 * ITEM, X + half * 256 * BT, 2, 0);
+        }
+    } else if (stage == 1) {                            // S3 (x H2): warps 0-3 Wfc1x | 4-15 Whh2 (rg, kc)
+        const int rg = w < 4 ? 0 : 1 + (w - 4) % 3, kc = w < 4 ? w : (w - 4) / 3;
+        e = make_int4(W + W_M3 + (rg * 4 + kc) * ITEM, X + kc * 128 * BT, 1, 0);
+    } else if (stage == 2) {                            // S4: warps 0-3 Wfc2x x Y1 | 4-15 conditioning items x cx
+        if (w < 4) e = make_int4(W + W_M4 + w * ITEM, X + w * 128 * BT, 1, 0);
+        else {
+            const int it = w - 4;
+            const int chunk = (it < 3) ? 0 : (it < 9) ? ((it - 3) & 1) : (it == 9) ? 0 : 1;
+            e = make_int4(W + w_mc(rows5) + it * ITEM, c.m.cx + chunk * 128 * BT, 1, 0);
+        }
+    } else {                                            // S5 (x Y2): rows5 / 4 row groups x 4 K chunks
+        if (w < rows5) e = make_int4(W + W_M5 + w * ITEM, X + (w & 3) * 128 * BT, 1, 0);
+    }
+    reinterpret_cast<int4 *>(c.sm + c.m.tab)[c.tid] = e;
+}
+
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel(const KParams prm)
 {
     extern __shared__ __align__(128) float sm[];
@@ -607,6 +635,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
     c.warp = c.tid >> 5;
     c.cta = blockIdx.x;
     c.cond_visit = 0;
+    c.tprev = 0;
     const KParams &p = prm;
     const int G = p.G, S = p.S;
     const int lane = c.lane, w = c.warp;
@@ -618,6 +647,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
         for (int i = c.tid; i < w_total(p.rows5) / 4; i += NTHREADS) dst[i] = src[i];
         for (int i = c.tid; i < CONDK * BT; i += NTHREADS) sm[c.m.cx + i] = 0.f;
         for (int i = c.tid; i < MAXG * PG_SIZE; i += NTHREADS) sm[c.m.priv + i] = 0.f;
+        build_work_table(c);
         if (c.tid == 0) {
             uint64_t *bar = reinterpret_cast<uint64_t *>(sm + c.m.mbar);
             mbar_init(bar, 1);
@@ -634,11 +664,12 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
                 pg[PG_GH2 + c.tid] = sv[SV_BHH2 + (c.tid >> 3)];
             }
         }
+        if (c.tid < 2 * PROF_SLOTS) sm[c.m.samp + 768 + c.tid] = 0.f;
         if (c.warp == NWARPS - 1) cond_issue(c, 0);
         __syncthreads();
         for (int g = 0; g < G; ++g) {
             cond_visit(c);
-            if (w >= 4) cond_items(c, w);
+            run_items(c, 2, w >= 4);
             __syncthreads();
             cond_finalize(c, g, w);
             if (w == 9) prefetch_draws(c, g, 0);
@@ -646,171 +677,123 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
         __syncthreads();
     }
 
+    if (p.prof && c.tid == 0) c.tprev = clock64();
+    const int cpairs = p.rows5 * p.nprod5 * BT;
     for (int t = 0; t <= S; ++t) {
         const unsigned epoch = (unsigned)t + 1u;
-        // ================= SA: sample step t-1, then GRU1 of step t ============================
-        for (int g = 0; g < G; ++g) {
-            float *pg = priv(c, g);
-            float *xb = xb_base(c, g);
-            if (t > 0) {
-                if (!cta_wait(c, g, 4, p.nprod5, (unsigned)t)) return;
-                gather_vec(sm + c.m.stage, xb + XB_LG, p.rows5 * p.nprod5 * BT / 4, c.tid);
-                __syncthreads();
-                if (p.mode == 0) sample_raw(c, g, t - 1);
-                else sample_mol(c, g, t - 1);
-                dump_logits(c, g, t - 1);
-                __syncthreads();
-                if (w == 9 && t < S) prefetch_draws(c, g, t);       // draws for the sample of step t
-            }
-            if (t < S && w == 0) {
-                // rnn1 GRU cell for this CTA's 4 units x 8 folds (torch gate order r, z, n)
-                const float *sv = small(c);
-                const int u = lane >> 3, f = lane & 7;
-                const float x = pg[PG_X + f];
-                const float gr = pg[PG_P1 + lane] + x * sv[SV_U1 + u] + sv[SV_B1 + u];
-                const float gz = pg[PG_P1 + 32 + lane] + x * sv[SV_U1 + 4 + u] + sv[SV_B1 + 4 + u];
-                const float gn = pg[PG_P1 + 64 + lane] + x * sv[SV_U1 + 8 + u] + sv[SV_B1 + 8 + u];
-                const float r = sigmoidf_(gr + pg[PG_GH1 + lane]);
-                const float z = sigmoidf_(gz + pg[PG_GH1 + 32 + lane]);
-                const float n = tanhf(gn + r * pg[PG_GH1 + 64 + lane]);
-                const float h = (1.0f - z) * n + z * pg[PG_H1 + lane];
-                pg[PG_H1 + lane] = h;
-                publish_line(xb + XB_H1, c.cta, lane, h);
-                raise_flag(flag_base(c, g, 0) + c.cta, epoch, lane);
-            }
-        }
-        if (t == S) break;
-        // ================= S2: rnn2 input side + rnn1 hidden side of the next step ============
-        for (int g = 0; g < G; ++g) {
-            float *pg = priv(c, g);
-            float *xb = xb_base(c, g);
-            if (!cta_wait(c, g, 0, NCTA, epoch)) return;
-            gather_vec(sm + c.m.stage, xb + XB_H1, VEC / 4, c.tid);
-            __syncthreads();
-            if (w < 12) {
-                const int rg = w % 6, half = w / 6;
-                float acc[4][BT];
-                zero_acc(acc);
-                const float *wi = sm + c.m.w + W_M2 + (rg * 4 + half * 2) * ITEM;
-                item_fma(wi, sm + c.m.stage, (half * 2) * 128, lane, acc);
-                item_fma(wi + ITEM, sm + c.m.stage, (half * 2 + 1) * 128, lane, acc);
-                sm[c.m.part + w * 32 + lane] = reduce_scatter32(acc, lane);
-            }
-            __syncthreads();
-            const float *part = sm + c.m.part;
-            const float *sv = small(c);
-            if (w == 0) {
-                const int u = lane >> 3, f = lane & 7;
-                const float x = pg[PG_X + f];
-                float gi[3];
-#pragma unroll
-                for (int q = 0; q < 3; ++q)
-                    gi[q] = (part[q * 32 + lane] + part[(6 + q) * 32 + lane]) + pg[PG_P2 + q * 32 + lane] + x * sv[SV_U2 + q * 4 + u] + sv[SV_B2 + q * 4 + u];
-                const float r = sigmoidf_(gi[0] + pg[PG_GH2 + lane]);
-                const float z = sigmoidf_(gi[1] + pg[PG_GH2 + 32 + lane]);
-                const float n = tanhf(gi[2] + r * pg[PG_GH2 + 64 + lane]);
-                const float h2 = (1.0f - z) * n + z * pg[PG_H2 + lane];
-                pg[PG_H2 + lane] = h2;
-                publish_line(xb + XB_H2, c.cta, lane, h2);
-                publish_line(xb + XB_S, c.cta, lane, pg[PG_H1 + lane] + h2);
-                raise_flag(flag_base(c, g, 1) + c.cta, epoch, lane);
-            } else if (w <= 3) {
-                const int q = w - 1;             // gh1 of the NEXT step: Whh1 . h1_t + b_hh1
-                pg[PG_GH1 + q * 32 + lane] = (part[(3 + q) * 32 + lane] + part[(9 + q) * 32 + lane]) + sv[SV_BHH1 + q * 4 + (lane >> 3)];
-            }
-        }
-        // ================= S3: fc1 + rnn2 hidden side of the next step =========================
-        for (int g = 0; g < G; ++g) {
-            float *pg = priv(c, g);
-            float *xb = xb_base(c, g);
-            if (!cta_wait(c, g, 1, NCTA, epoch)) return;
-            gather_vec(sm + c.m.stage, xb + XB_H2, VEC / 4, c.tid);
-            gather_vec(sm + c.m.stage + VEC, xb + XB_S, VEC / 4, c.tid);
-            __syncthreads();
-            {
-                float acc[4][BT];
-                zero_acc(acc);
-                if (w < 4) item_fma(sm + c.m.w + W_M3 + w * ITEM, sm + c.m.stage + VEC, w * 128, lane, acc);
-                else {
-                    const int rg = 1 + (w - 4) % 3, kc = (w - 4) / 3;
-                    item_fma(sm + c.m.w + W_M3 + (rg * 4 + kc) * ITEM, sm + c.m.stage, kc * 128, lane, acc);
-                }
-                sm[c.m.part + w * 32 + lane] = reduce_scatter32(acc, lane);
-            }
-            __syncthreads();
-            const float *part = sm + c.m.part;
-            const float *sv = small(c);
-            if (w == 0) {
-                const int u = lane >> 3, f = lane & 7;
-                float y = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + pg[PG_P3 + lane] + pg[PG_X + f] * sv[SV_U3 + u] + sv[SV_B3 + u];
-                y = fmaxf(y, 0.f);
-                publish_line(xb + XB_Y1, c.cta, lane, y);
-                raise_flag(flag_base(c, g, 2) + c.cta, epoch, lane);
-            } else if (w <= 3) {
-                const int q = w - 1;             // gh2 of the NEXT step
-                const int s0 = 4 + q;
-                pg[PG_GH2 + q * 32 + lane] = ((part[s0 * 32 + lane] + part[(s0 + 3) * 32 + lane]) + (part[(s0 + 6) * 32 + lane] + part[(s0 + 9) * 32 + lane])) + sv[SV_BHH2 + q * 4 + (lane >> 3)];
-            }
-        }
-        // ================= S4: fc2 + conditioning projections of step t+1 ======================
-        for (int g = 0; g < G; ++g) {
-            float *pg = priv(c, g);
-            float *xb = xb_base(c, g);
-            cond_visit(c);                       // stages cond(t+1) of this group, prefetches the next visit
-            if (!cta_wait(c, g, 2, NCTA, epoch)) return;
-            gather_vec(sm + c.m.stage, xb + XB_Y1, VEC / 4, c.tid);
-            __syncthreads();
-            if (w < 4) {
-                float acc[4][BT];
-                zero_acc(acc);
-                item_fma(sm + c.m.w + W_M4 + w * ITEM, sm + c.m.stage, w * 128, lane, acc);
-                sm[c.m.part + w * 32 + lane] = reduce_scatter32(acc, lane);
-            } else if (t + 1 < S) cond_items(c, w);
-            __syncthreads();
-            const float *part = sm + c.m.part;
-            const float *sv = small(c);
-            if (w == 0) {
-                const int u = lane >> 3;
-                float y = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + pg[PG_P4 + lane] + sv[SV_B4 + u];
-                y = fmaxf(y, 0.f);
-                publish_line(xb + XB_Y2, c.cta, lane, y);
-                raise_flag(flag_base(c, g, 3) + c.cta, epoch, lane);
-            }
-            __syncwarp();
-            if (t + 1 < S) {
-                if (w == 0) pg[PG_P4 + lane] = part[(4 + 11) * 32 + lane];
-                else if (w != 8) cond_finalize(c, g, w);
-            }
-        }
-        // ================= S5: output projection =================================================
-        if (c.cta < p.nprod5) {
+        // stage 0 = SA (sample step t-1, GRU1 of step t); 1..4 = S2..S5.  Groups are visited in a
+        // static order inside each stage so one group's exchange overlaps the others' mat-vecs.
+        for (int stage = 0; stage < 5; ++stage) {
+            if (stage == 4 && c.cta >= p.nprod5) break;            // only the logits producers run S5
             for (int g = 0; g < G; ++g) {
-                float *xb = xb_base(c, g);
-                if (!cta_wait(c, g, 3, NCTA, epoch)) return;
-                gather_vec(sm + c.m.stage, xb + XB_Y2, VEC / 4, c.tid);
-                __syncthreads();
-                if (w < p.rows5) {
-                    float acc[4][BT];
-                    zero_acc(acc);
-                    item_fma(sm + c.m.w + W_M5 + w * ITEM, sm + c.m.stage, (w & 3) * 128, lane, acc);
-                    sm[c.m.part + w * 32 + lane] = reduce_scatter32(acc, lane);
+                float *pg = priv(c, g);
+                unsigned long long *xb = xb_base(c, g);
+                const float *sv = small(c);
+                const float *part = sm + c.m.part;
+                if (stage == 0) {
+                    if (t > 0) {
+                        if (!cta_gather(c, xb + XB_LG, cpairs, (unsigned)t)) return;
+                        tick(c, 0);
+                        if (p.mode != 0) sample_mol(c, g, t - 1);
+                        else if (p.C > 512) sample_raw<2>(c, g, t - 1);
+                        else sample_raw<1>(c, g, t - 1);
+                        dump_logits(c, g, t - 1);
+                        __syncthreads();
+                        tick(c, 1);
+                        if (w == 9 && t < S) prefetch_draws(c, g, t);   // draws for the sample of step t
+                    }
+                    if (t < S && w == 0) {
+                        // rnn1 GRU cell for this CTA's 4 units x 8 folds (torch gate order r, z, n)
+                        const int u = lane >> 3, f = lane & 7;
+                        const float x = pg[PG_X + f];
+                        const float gr = pg[PG_P1 + lane] + x * sv[SV_U1 + u] + sv[SV_B1 + u];
+                        const float gz = pg[PG_P1 + 32 + lane] + x * sv[SV_U1 + 4 + u] + sv[SV_B1 + 4 + u];
+                        const float gn = pg[PG_P1 + 64 + lane] + x * sv[SV_U1 + 8 + u] + sv[SV_B1 + 8 + u];
+                        const float r = sigmoidf_(gr + pg[PG_GH1 + lane]);
+                        const float z = sigmoidf_(gz + pg[PG_GH1 + 32 + lane]);
+                        const float n = tanhf(gn + r * pg[PG_GH1 + 64 + lane]);
+                        const float h = (1.0f - z) * n + z * pg[PG_H1 + lane];
+                        pg[PG_H1 + lane] = h;
+                        publish_line(xb + XB_H1, c.cta, lane, h, epoch);
+                        tick(c, 2);
+                    }
+                    continue;
                 }
-                __syncthreads();
-                if (w * 4 < p.rows5) {
-                    const float *part = sm + c.m.part + w * 128;
-                    const float *sv = small(c);
-                    const float v = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + sv[SV_B5 + w * 4 + (lane >> 3)];
-                    const int k = p.rows5 * c.cta + w * 4 + (lane >> 3);
-                    st_cg(xb + XB_LG + xidx(k, lane & 7), v);
+                if (t == S) break;
+                if (stage == 3) {
+                    cond_visit(c);               // stages cond(t+1) of this group, prefetches the next visit
+                    tick(c, 9);
                 }
-                if (p.rows5 > 4) __syncthreads();
-                if (w == 0) raise_flag(flag_base(c, g, 4) + c.cta, epoch, lane);
+                if (!cta_gather(c, xb + (stage - 1) * VEC, VEC, epoch)) return;      // H1 | H2 | Y1 | Y2
+                tick(c, 3 * stage + (stage == 3 ? 1 : 0) + (stage == 4 ? 1 : 0));
+                run_items(c, stage - 1, stage != 3 || w < 4 || t + 1 < S);
+                __syncthreads();
+                tick(c, 3 * stage + 1 + (stage == 3 ? 1 : 0) + (stage == 4 ? 1 : 0));
+                if (stage == 1) {
+                    // S2: rnn2 cell; gh1 of the next step; Wfc1x . h1
+                    if (w == 0) {
+                        const int u = lane >> 3, f = lane & 7;
+                        const float x = pg[PG_X + f];
+                        float gi[3];
+#pragma unroll
+                        for (int q = 0; q < 3; ++q)
+                            gi[q] = (part[q * 32 + lane] + part[(7 + q) * 32 + lane]) + pg[PG_P2 + q * 32 + lane] + x * sv[SV_U2 + q * 4 + u] + sv[SV_B2 + q * 4 + u];
+                        const float r = sigmoidf_(gi[0] + pg[PG_GH2 + lane]);
+                        const float z = sigmoidf_(gi[1] + pg[PG_GH2 + 32 + lane]);
+                        const float n = tanhf(gi[2] + r * pg[PG_GH2 + 64 + lane]);
+                        const float h2 = (1.0f - z) * n + z * pg[PG_H2 + lane];
+                        pg[PG_H2 + lane] = h2;
+                        publish_line(xb + XB_H2, c.cta, lane, h2, epoch);
+                        tick(c, 5);
+                    } else if (w <= 3) {
+                        const int q = w - 1;     // gh1 of the NEXT step: Whh1 . h1_t + b_hh1
+                        pg[PG_GH1 + q * 32 + lane] = (part[(3 + q) * 32 + lane] + part[(10 + q) * 32 + lane]) + sv[SV_BHH1 + q * 4 + (lane >> 3)];
+                    } else if (w == 4) {
+                        pg[PG_F1 + lane] = part[6 * 32 + lane] + part[13 * 32 + lane];      // Wfc1x . h1_t
+                    }
+                } else if (stage == 2) {
+                    // S3: fc1 (h2 part + saved h1 part); gh2 of the next step
+                    if (w == 0) {
+                        const int u = lane >> 3, f = lane & 7;
+                        float y = (((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + pg[PG_F1 + lane]) + pg[PG_P3 + lane] + pg[PG_X + f] * sv[SV_U3 + u] + sv[SV_B3 + u];
+                        y = fmaxf(y, 0.f);
+                        publish_line(xb + XB_Y1, c.cta, lane, y, epoch);
+                        tick(c, 8);
+                    } else if (w <= 3) {
+                        const int q = w - 1, s0 = 4 + q;
+                        pg[PG_GH2 + q * 32 + lane] = ((part[s0 * 32 + lane] + part[(s0 + 3) * 32 + lane]) + (part[(s0 + 6) * 32 + lane] + part[(s0 + 9) * 32 + lane])) + sv[SV_BHH2 + q * 4 + (lane >> 3)];
+                    }
+                } else if (stage == 3) {
+                    // S4: fc2; conditioning projections of step t+1
+                    if (w == 0) {
+                        float y = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + pg[PG_P4 + lane] + sv[SV_B4 + (lane >> 3)];
+                        y = fmaxf(y, 0.f);
+                        publish_line(xb + XB_Y2, c.cta, lane, y, epoch);
+                        tick(c, 12);
+                    }
+                    __syncwarp();
+                    if (t + 1 < S) {
+                        if (w == 0) pg[PG_P4 + lane] = part[(4 + 11) * 32 + lane];
+                        else if (w != 8) cond_finalize(c, g, w);
+                    }
+                } else {
+                    // S5: logits of this CTA's rows5 classes
+                    if (w * 4 < p.rows5) {
+                        const float *pw = part + w * 128;
+                        const float v = ((pw[lane] + pw[32 + lane]) + (pw[64 + lane] + pw[96 + lane])) + sv[SV_B5 + w * 4 + (lane >> 3)];
+                        const int k = p.rows5 * c.cta + w * 4 + (lane >> 3);
+                        st_pair(xb + XB_LG + k * BT + (lane & 7), v, epoch);
+                    }
+                    tick(c, 15);
+                }
             }
         }
     }
+    if (p.prof && c.tid == 0)
+        for (int i = 0; i < PROF_SLOTS; ++i) p.prof[(size_t)c.cta * PROF_SLOTS + i] = reinterpret_cast<long long *>(sm + c.m.samp + 768)[i];
 }
 
-// Exchange microbenchmark: the same publish / poll / gather sequence on an empty kernel.
+// Exchange microbenchmark: the same publish / LL-gather sequence on an otherwise empty kernel.
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe_kernel(const KParams prm)
 {
     extern __shared__ __align__(128) float sm[];
@@ -824,19 +807,15 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe
     c.cta = blockIdx.x;
     if (c.tid == 0) *reinterpret_cast<int *>(sm + c.m.mbar + 6) = 0;
     __syncthreads();
-    float *xb = xb_base(c, 0);
+    unsigned long long *xb = xb_base(c, 0);
     float acc = 0.f;
     for (int it = 0; it < prm.probe_iters; ++it) {
-        const int e = it % NEXCH;
-        const unsigned epoch = (unsigned)(it / NEXCH) + 1u;
-        if (c.warp == 0) {
-            publish_line(xb + XB_H1, c.cta, c.lane, acc + (float)it);
-            raise_flag(flag_base(c, 0, e) + c.cta, epoch, c.lane);
-        }
-        if (!cta_wait(c, 0, e, NCTA, epoch)) return;
-        gather_vec(sm + c.m.stage, xb + XB_H1, VEC / 4, c.tid);
+        unsigned long long *vec = xb + (it & 3) * VEC;
+        const unsigned epoch = (unsigned)it + 1u;
+        if (c.warp == 0) publish_line(vec, c.cta, c.lane, acc + (float)it, epoch);
+        if (!cta_gather(c, vec, VEC, epoch)) return;
+        acc += sm[c.m.stage + c.tid] * 1e-30f;
         __syncthreads();
-        acc += sm[c.m.stage + c.tid];
     }
     if (acc == 123.456f) prm.status[1] = 1;      // keep the loads alive
 }

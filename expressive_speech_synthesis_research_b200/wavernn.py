@@ -117,6 +117,16 @@ class _Engine:
         _lib.check(self.lib.wrnn_get_info(self.handle, ctypes.byref(out)))
         return out
 
+    def stage_cycles(self, enable=None):
+        """enable=True/False toggles in-kernel stage timing; None returns the last launch's counters
+        as an int64 array [128, 24]."""
+        if enable is not None:
+            _lib.check(self.lib.wrnn_set_profiling(self.handle, int(bool(enable))))
+            return None
+        out = np.zeros((128, 24), dtype=np.int64)
+        _lib.check(self.lib.wrnn_get_stage_cycles(self.handle, out.ctypes.data, out.size))
+        return out
+
     def measure_exchange(self, iters=2000):
         us = ctypes.c_float()
         _lib.check(self.lib.wrnn_measure_exchange(self.handle, iters, ctypes.byref(us)))
@@ -199,8 +209,19 @@ class WaveRNN(nn.Module):
     def conditioning(self, mels):
         """generate() prologue, fatchord_version.py:162-165: (1, feat, T) -> (L, feat), (L, 4*aux)."""
         m = F.pad(mels, (self.pad, self.pad))                       # pad_tensor(side='both'), :260-270
-        m, aux = self.upsample(m)
+        m, aux = self.upsample_fp32(m)
         return m[0].contiguous(), aux[0].contiguous()
+
+    def upsample_fp32(self, m):
+        """UpsampleNetwork in true fp32: cuDNN's default TF32 convolutions would put ~1e-3 relative
+        error into the conditioning, visible as 4e-5 on the logits (measured on B200)."""
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                return self.upsample(m)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
 
     # ------------------------------------------------------------------ the hot path
     def generate(self, mels, *args, uniforms=None, seed=None, forced_x=None, return_logits=False,

@@ -144,8 +144,16 @@ typedef struct {
 } wrnn_info;
 int32_t wrnn_get_info(wrnn_handle *h, wrnn_info *out);
 
-/* Microbenchmark of the grid-level exchange used by the step loop (publish 128 B + flag,
- * poll 128 flags, gather 16 KiB), `iters` times on an otherwise empty persistent kernel.
+/* Optional in-kernel stage timing (development / profiles/): when enabled, thread 0 of every
+ * CTA accumulates clock64() cycles per (stage, phase) of the step loop; the counters of the
+ * last wrnn_generate_folds launch are returned as int64 [128 CTAs][24 slots]
+ * (slot map in csrc/wavernn_kernel.cuh).  Adds ~20 clock reads per step. */
+int32_t wrnn_set_profiling(wrnn_handle *h, int32_t enable);
+int32_t wrnn_get_stage_cycles(wrnn_handle *h, int64_t *out /* [host] */, int32_t n);
+
+/* Microbenchmark of the grid-level exchange used by the step loop (each CTA publishes 32
+ * {value, epoch} pairs, then polls / gathers the 4096 pairs of the whole vector from L2),
+ * `iters` times on an otherwise empty persistent kernel.
  * Writes the mean device time per exchange in microseconds.  Synchronous. */
 int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *usec_per_exchange);
 

@@ -108,7 +108,7 @@ def test_teacher_forced_logits_vs_reference_forward(mode):
     B, seq = x.shape
     with torch.no_grad():
         m.eval()
-        mu, aux = m.upsample(mel.cuda())                   # forward(): no extra padding (fatchord_version.py:124)
+        mu, aux = m.upsample_fp32(mel.cuda())              # forward(): no extra padding (fatchord_version.py:124)
         m.train()
     forced = np.concatenate([x[:, 1:], np.zeros((B, 1), np.float32)], 1).T.copy()
     U = synth.make_uniforms(seq, B, mode).numpy()
