@@ -60,7 +60,7 @@ __host__ __device__ inline SmemMap smem_map(int rows5)
     SmemMap m;
     m.w = 0;
     m.stage = m.w + w_total(rows5);
-    m.cx = m.stage + (rows5 > 4 ? 2 : 1) * VEC;     // 1024-class logits need 8192 floats
+    m.cx = m.stage + (rows5 > 4 ? 9248 : 5152);     // >= VEC, and the fold-major logits image 8 x lg_row(C/32)
     m.cstage = m.cx + CONDK * BT;
     m.part = m.cstage + 2 * BT * 208;
     m.priv = m.part + NWARPS * 32;
@@ -150,35 +150,42 @@ __device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * (1.0
 
 constexpr int POLL_CAP = 1 << 22;    // watchdog: ~1 s of polling
 
+// Fold-major shared-memory image of the RAW logits used by the sampler: fold f's classes are
+// contiguous, NPL = C/32 per lane with 4 floats of padding per lane (conflict-free LDS.128) and 4
+// more per fold row (conflict-free scatter from the LL gather).
+__host__ __device__ constexpr int lg_row(int npl) { return 32 * (npl + 4) + 4; }
+__device__ __forceinline__ int lg_idx(int npl, int k, int f) { return f * lg_row(npl) + (k / npl) * (npl + 4) + (k % npl); }
+
 // LL gather of `npairs` (multiple of 2) {value, epoch} pairs from L2 into the swizzled [k][8]
 // shared-memory layout; each thread polls its own 16-byte chunks until both epochs match.
 // Returns false if the watchdog fired (thread-local; the caller makes it CTA-uniform).
-__device__ __forceinline__ bool gather_ll(float *dst, const unsigned long long *src, int npairs, unsigned epoch, int tid)
+__device__ __forceinline__ bool gather_ll(float *dst, const unsigned long long *src, int npairs, unsigned epoch, int tid, int npl = 0)
 {
     bool ok = true;
-    if (npairs == VEC) {
+    const int nchunks = npairs >> 1;               // 16-byte chunks of two pairs: class/unit k = i / 4, folds 2*(i%4), +1
+    for (int base = 0; base < nchunks; base += 4 * NTHREADS) {
         uint4 v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = ld_pairs2(src + 2 * (tid + j * NTHREADS));
+        for (int j = 0; j < 4; ++j) {              // all loads in flight before the first epoch check
+            const int i = base + tid + j * NTHREADS;
+            if (i < nchunks) v[j] = ld_pairs2(src + 2 * i);
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int i = tid + j * NTHREADS;              // chunk: k = i / 4, folds 2*(i%4), +1
-            int spin = 0;
-            while (v[j].y != epoch || v[j].w != epoch) {
-                if (++spin > POLL_CAP) { ok = false; break; }
-                v[j] = ld_pairs2(src + 2 * i);
+            const int i = base + tid + j * NTHREADS;
+            if (i < nchunks) {
+                int spin = 0;
+                while (v[j].y != epoch || v[j].w != epoch) {
+                    if (++spin > POLL_CAP) { ok = false; break; }
+                    v[j] = ld_pairs2(src + 2 * i);
+                }
+                const int k = i >> 2, f0 = (i & 3) * 2;
+                if (npl == 0) *reinterpret_cast<float2 *>(dst + xidx(k, f0)) = make_float2(__uint_as_float(v[j].x), __uint_as_float(v[j].z));
+                else {
+                    dst[lg_idx(npl, k, f0)] = __uint_as_float(v[j].x);
+                    dst[lg_idx(npl, k, f0 + 1)] = __uint_as_float(v[j].z);
+                }
             }
-            *reinterpret_cast<float2 *>(dst + xidx(i >> 2, (i & 3) * 2)) = make_float2(__uint_as_float(v[j].x), __uint_as_float(v[j].z));
-        }
-    } else {
-        for (int i = tid; i < npairs / 2; i += NTHREADS) {
-            uint4 v = ld_pairs2(src + 2 * i);
-            int spin = 0;
-            while (v.y != epoch || v.w != epoch) {
-                if (++spin > POLL_CAP) { ok = false; break; }
-                v = ld_pairs2(src + 2 * i);
-            }
-            *reinterpret_cast<float2 *>(dst + xidx(i >> 2, (i & 3) * 2)) = make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
         }
     }
     return ok;
@@ -282,10 +289,10 @@ __device__ __forceinline__ unsigned long long *xb_base(const Ctx &c, int g)
 
 // LL-gather one exchanged vector of group g into the staging buffer; CTA-uniform result
 // (false = watchdog fired somewhere in this CTA; the kernel then exits and the host reports it).
-__device__ __forceinline__ bool cta_gather(Ctx &c, const unsigned long long *src, int npairs, unsigned epoch)
+__device__ __forceinline__ bool cta_gather(Ctx &c, const unsigned long long *src, int npairs, unsigned epoch, int npl = 0)
 {
     int *abort_flag = reinterpret_cast<int *>(c.sm + c.m.mbar + 6);
-    if (!gather_ll(c.sm + c.m.stage, src, npairs, epoch, c.tid)) {
+    if (!gather_ll(c.sm + c.m.stage, src, npairs, epoch, c.tid, npl)) {
         *abort_flag = 1;
         atomicExch(c.p->status, -4);
     }
@@ -389,139 +396,64 @@ __device__ __forceinline__ void prefetch_draws(Ctx &c, int g, int step)
     }
 }
 
-// ---- sampling (all threads): logits of step s are in c.sm[stage]; writes x into priv ---------
-template <int NBI>
+// ---- sampling: logits of step s are in c.sm[stage]; writes the fed-back x into priv ----------
+// RAW: softmax (fatchord_version.py:211) + inverse CDF with one uniform per fold (oracle/ref_shim.py:
+// k = #{c : cdf_c <= u}, clamped) + label -> float (:214).  One warp per fold, NPL = C/32 consecutive
+// classes per lane, warp shuffles only (no block barrier).
+template <int NPL>
 __device__ __forceinline__ void sample_raw(Ctx &c, int g, int s)
 {
     const KParams &p = *c.p;
-    const float *lg = c.sm + c.m.stage;
-    float *sc = c.sm + c.m.samp;                 // [0,256) block max, [256,512) block sum, 512.. owner, 520.. thr, 528.. label
+    if (c.warp >= BT) return;
     float *pg = priv(c, g);
-    const int lane = c.lane, f = lane & 7, cs = lane >> 3;
-    const int nblk = p.C >> 5;
-    float e[NBI][8];
+    const int lane = c.lane, f = c.warp;
+    const float *row = c.sm + c.m.stage + f * lg_row(NPL) + lane * (NPL + 4);
+    float v[NPL];
+    if (NPL >= 4) {
 #pragma unroll
-    for (int bi = 0; bi < NBI; ++bi) {
-        const int blk = c.warp + bi * NWARPS;
-        if (blk < nblk) {
-            float v[8], bm = -INFINITY;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                v[m] = lg[xidx(32 * blk + 4 * m + cs, f)];
-                bm = fmaxf(bm, v[m]);
-            }
-            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 8));
-            bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
-            float ls = 0.f;
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                e[bi][m] = expf(v[m] - bm);
-                ls += e[bi][m];
-            }
-            ls += __shfl_xor_sync(0xffffffffu, ls, 8);
-            ls += __shfl_xor_sync(0xffffffffu, ls, 16);
-            if (cs == 0) {
-                sc[blk * 8 + f] = bm;
-                sc[256 + blk * 8 + f] = ls;
-            }
+        for (int j = 0; j < NPL; j += 4) {
+            const float4 q = *reinterpret_cast<const float4 *>(row + j);
+            v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
         }
+    } else {
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) v[j] = row[j];
     }
-    __syncthreads();
-    if (c.warp == 0) {
-        // lane (f, cs) owns blocks cs*8 .. cs*8+7 (block order == class order)
-        float bmx[8], bsum[8], M = -INFINITY;
+    float m = v[0];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int blk = cs * 8 + j;
-            bmx[j] = (blk < nblk) ? sc[blk * 8 + f] : -INFINITY;
-            bsum[j] = (blk < nblk) ? sc[256 + blk * 8 + f] : 0.f;
-            M = fmaxf(M, bmx[j]);
-        }
-        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 8));
-        M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, 16));
-        float scale[8], pre[8], run = 0.f;
+    for (int j = 1; j < NPL; ++j) m = fmaxf(m, v[j]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            scale[j] = (cs * 8 + j < nblk) ? expf(bmx[j] - M) : 0.f;
-            pre[j] = run;                       // scaled mass of this lane's blocks before block j
-            run += bsum[j] * scale[j];
-        }
-        // exclusive scan of `run` over the four cs lanes of this fold
-        const float r1 = __shfl_up_sync(0xffffffffu, run, 8), r2 = __shfl_up_sync(0xffffffffu, run, 16),
-                    r3 = __shfl_up_sync(0xffffffffu, run, 24);
-        const float base = (cs >= 1 ? r1 : 0.f) + (cs >= 2 ? r2 : 0.f) + (cs >= 3 ? r3 : 0.f);
-        const float tot = __shfl_sync(0xffffffffu, base + run, 24 + f);
-        const float thr = pg[PG_U + f * 11] * tot;
-        int own = 1 << 20;
-        float thr_local = INFINITY;
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    float run = 0.f;                              // inclusive prefix inside the lane
 #pragma unroll
-        for (int j = 7; j >= 0; --j) {
-            const int blk = cs * 8 + j;
-            if (blk < nblk && base + pre[j] + bsum[j] * scale[j] > thr) {
-                own = blk;
-                thr_local = (thr - (base + pre[j])) / scale[j];
-            }
-        }
-        // first owning block over the cs lanes
-#pragma unroll
-        for (int off = 8; off <= 16; off <<= 1) {
-            const int o2 = __shfl_xor_sync(0xffffffffu, own, off);
-            const float t2 = __shfl_xor_sync(0xffffffffu, thr_local, off);
-            if (o2 < own) {
-                own = o2;
-                thr_local = t2;
-            }
-        }
-        if (cs == 0) {
-            if (own >= nblk) {                   // u * total beyond the last prefix: clamp to the last class
-                own = nblk - 1;
-                thr_local = INFINITY;
-            }
-            sc[512 + f] = __int_as_float(own);
-            sc[520 + f] = thr_local;
-        }
+    for (int j = 0; j < NPL; ++j) {
+        run += expf(v[j] - m);
+        v[j] = run;
     }
-    __syncthreads();
-    {
-        const int own = __float_as_int(sc[512 + f]);
-        const float thr_local = sc[520 + f];
+    float incl = run;                             // inclusive scan of the lane totals across the warp
 #pragma unroll
-        for (int bi = 0; bi < NBI; ++bi) {
-            const int blk = c.warp + bi * NWARPS;
-            if (blk < nblk) {                    // warp-uniform
-                float rowbase = 0.f;
-                int cnt = 0;
-#pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    const float a1 = __shfl_up_sync(0xffffffffu, e[bi][m], 8), a2 = __shfl_up_sync(0xffffffffu, e[bi][m], 16),
-                                a3 = __shfl_up_sync(0xffffffffu, e[bi][m], 24);
-                    const float incl = ((cs >= 3 ? a3 : 0.f) + (cs >= 2 ? a2 : 0.f)) + (cs >= 1 ? a1 : 0.f) + e[bi][m];
-                    float rs = e[bi][m] + __shfl_xor_sync(0xffffffffu, e[bi][m], 8);
-                    rs += __shfl_xor_sync(0xffffffffu, rs, 16);
-                    cnt += (rowbase + incl <= thr_local) ? 1 : 0;
-                    rowbase += rs;
-                }
-                cnt += __shfl_xor_sync(0xffffffffu, cnt, 8);
-                cnt += __shfl_xor_sync(0xffffffffu, cnt, 16);
-                if (cs == 0 && own == blk) {
-                    int k = 32 * blk + cnt;
-                    k = k > p.C - 1 ? p.C - 1 : k;
-                    sc[528 + f] = __int_as_float(k);
-                }
-            }
-        }
+    for (int off = 1; off < 32; off <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
     }
-    __syncthreads();
-    if (c.warp == 0 && lane < BT) {
-        const int k = __float_as_int(sc[528 + lane]);
+    const float excl = incl - run;
+    const float total = __shfl_sync(0xffffffffu, incl, 31);
+    const float thr = pg[PG_U + f * 11] * total;
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < NPL; ++j) cnt += (excl + v[j] <= thr) ? 1 : 0;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+    if (lane == 0) {
+        const int k = cnt > p.C - 1 ? p.C - 1 : cnt;
         // 2 * k.float() / (C - 1.) - 1.  (fatchord_version.py:214), three separately rounded fp32 ops
         const float sample = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, (float)k), (float)p.C - 1.0f), 1.0f);
-        if (lane < p.group_nf[g] && c.cta == (s * p.G + g) % NCTA) {
-            const int b = p.group_fold0[g] + lane;
+        if (f < p.group_nf[g] && c.cta == (s * p.G + g) % NCTA) {
+            const int b = p.group_fold0[g] + f;
             p.samples_out[(size_t)b * p.S + s] = sample;
             if (p.labels_out) p.labels_out[(size_t)b * p.S + s] = k;
         }
-        pg[PG_X + lane] = p.forced_x ? pg[PG_FX + lane] : sample;
+        pg[PG_X + f] = p.forced_x ? pg[PG_FX + f] : sample;
     }
 }
 
@@ -575,9 +507,10 @@ __device__ __forceinline__ void dump_logits(Ctx &c, int g, int s)
     const KParams &p = *c.p;
     if (!p.logits_out || c.cta != (s * p.G + g) % NCTA) return;
     const float *lg = c.sm + c.m.stage;
+    const int npl = p.mode == 0 ? p.C >> 5 : 0;
     for (int f = 0; f < p.group_nf[g]; ++f) {
         float *dst = p.logits_out + ((size_t)s * p.B + p.group_fold0[g] + f) * p.C;
-        for (int k = c.tid; k < p.C; k += NTHREADS) dst[k] = lg[xidx(k, f)];
+        for (int k = c.tid; k < p.C; k += NTHREADS) dst[k] = npl ? lg[lg_idx(npl, k, f)] : lg[xidx(k, f)];
     }
 }
 
@@ -692,11 +625,16 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
                 const float *part = sm + c.m.part;
                 if (stage == 0) {
                     if (t > 0) {
-                        if (!cta_gather(c, xb + XB_LG, cpairs, (unsigned)t)) return;
+                        if (!cta_gather(c, xb + XB_LG, cpairs, (unsigned)t, p.mode == 0 ? p.C >> 5 : 0)) return;
                         tick(c, 0);
                         if (p.mode != 0) sample_mol(c, g, t - 1);
-                        else if (p.C > 512) sample_raw<2>(c, g, t - 1);
-                        else sample_raw<1>(c, g, t - 1);
+                        else switch (p.C) {
+                            case 1024: sample_raw<32>(c, g, t - 1); break;
+                            case 512: sample_raw<16>(c, g, t - 1); break;
+                            case 256: sample_raw<8>(c, g, t - 1); break;
+                            case 128: sample_raw<4>(c, g, t - 1); break;
+                            default: sample_raw<2>(c, g, t - 1); break;
+                        }
                         dump_logits(c, g, t - 1);
                         __syncthreads();
                         tick(c, 1);
