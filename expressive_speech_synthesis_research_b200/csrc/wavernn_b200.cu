@@ -139,6 +139,7 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
     }
     H_TRY(cudaFuncSetAttribute(wavernn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     H_TRY(cudaFuncSetAttribute(wavernn_exchange_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    H_TRY(cudaFuncSetAttribute(wavernn_persistent_kernel_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
     int occ = 0;
     H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wavernn_persistent_kernel, NTHREADS, h->smem_bytes));
     if (occ < 1) {
@@ -333,7 +334,9 @@ static int32_t launch_chunk(wrnn_handle *h, KParams &p, cudaStream_t st, bool pr
     CUDA_TRY(cudaMemsetAsync(h->xb, 0, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
     CUDA_TRY(cudaEventRecord(h->ev0, st));
-    CUDA_TRY(cudaLaunchCooperativeKernel(probe ? (const void *)wavernn_exchange_probe_kernel : (const void *)wavernn_persistent_kernel,
+    const void *fn = probe ? (const void *)wavernn_exchange_probe_kernel
+                           : (p.prof ? (const void *)wavernn_persistent_kernel_prof : (const void *)wavernn_persistent_kernel);
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn,
                                          dim3(NCTA), dim3(NTHREADS), args, (size_t)h->smem_bytes, st));
     CUDA_TRY(cudaEventRecord(h->ev1, st));
     CUDA_TRY(cudaStreamSynchronize(st));

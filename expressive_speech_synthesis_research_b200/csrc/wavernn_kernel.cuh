@@ -53,7 +53,7 @@ constexpr int PG_GH1 = 0, PG_GH2 = 96, PG_P1 = 192, PG_P2 = 288, PG_P3 = 384, PG
 
 // ---- shared memory map (floats) -----------------------------------------------------------
 struct SmemMap {
-    int w, stage, cx, cstage, part, priv, samp, tab, mbar, total;
+    int w, stage, cx, cstage, part, priv, samp, tab, mbar, raw, total;
 };
 __host__ __device__ inline SmemMap smem_map(int rows5)
 {
@@ -66,8 +66,9 @@ __host__ __device__ inline SmemMap smem_map(int rows5)
     m.priv = m.part + NWARPS * 32;
     m.samp = m.priv + MAXG * PG_SIZE;
     m.tab = m.samp + 1024;                          // work table: 4 item stages x 16 warps x int4
-    m.mbar = m.tab + 4 * NWARPS * 4;
-    m.total = m.mbar + 8;
+    m.mbar = m.tab + 4 * NWARPS * 4;                // [0..3] cond mbarriers, [4,5] cond masks, [6] abort, [8,9] prefetch mbarrier
+    m.raw = m.mbar + 16;                            // TMA prefetch target: one exchanged vector as raw LL pairs (32 KiB)
+    m.total = m.raw + (rows5 > 4 ? 0 : 2 * VEC);    // (1024-class models run without the prefetch buffer)
     return m;
 }
 
@@ -136,7 +137,7 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
 // Philox4x32-10 (Salmon et al. 2011): counter-based RNG for the in-kernel uniforms
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
 {
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 10; ++i) {
         unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
         unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
@@ -154,43 +155,15 @@ constexpr int POLL_CAP = 1 << 22;    // watchdog: ~1 s of polling
 // contiguous, NPL = C/32 per lane with 4 floats of padding per lane (conflict-free LDS.128) and 4
 // more per fold row (conflict-free scatter from the LL gather).
 __host__ __device__ constexpr int lg_row(int npl) { return 32 * (npl + 4) + 4; }
-__device__ __forceinline__ int lg_idx(int npl, int k, int f) { return f * lg_row(npl) + (k / npl) * (npl + 4) + (k % npl); }
+__device__ __forceinline__ int lg_idx(int npl, int k, int f)       // npl is a power of two
+{
+    const int sh = 31 - __clz(npl);
+    return f * lg_row(npl) + (k >> sh) * (npl + 4) + (k & (npl - 1));
+}
 
 // LL gather of `npairs` (multiple of 2) {value, epoch} pairs from L2 into the swizzled [k][8]
 // shared-memory layout; each thread polls its own 16-byte chunks until both epochs match.
 // Returns false if the watchdog fired (thread-local; the caller makes it CTA-uniform).
-__device__ __forceinline__ bool gather_ll(float *dst, const unsigned long long *src, int npairs, unsigned epoch, int tid, int npl = 0)
-{
-    bool ok = true;
-    const int nchunks = npairs >> 1;               // 16-byte chunks of two pairs: class/unit k = i / 4, folds 2*(i%4), +1
-    for (int base = 0; base < nchunks; base += 4 * NTHREADS) {
-        uint4 v[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {              // all loads in flight before the first epoch check
-            const int i = base + tid + j * NTHREADS;
-            if (i < nchunks) v[j] = ld_pairs2(src + 2 * i);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int i = base + tid + j * NTHREADS;
-            if (i < nchunks) {
-                int spin = 0;
-                while (v[j].y != epoch || v[j].w != epoch) {
-                    if (++spin > POLL_CAP) { ok = false; break; }
-                    v[j] = ld_pairs2(src + 2 * i);
-                }
-                const int k = i >> 2, f0 = (i & 3) * 2;
-                if (npl == 0) *reinterpret_cast<float2 *>(dst + xidx(k, f0)) = make_float2(__uint_as_float(v[j].x), __uint_as_float(v[j].z));
-                else {
-                    dst[lg_idx(npl, k, f0)] = __uint_as_float(v[j].x);
-                    dst[lg_idx(npl, k, f0 + 1)] = __uint_as_float(v[j].z);
-                }
-            }
-        }
-    }
-    return ok;
-}
-
 // One work item: acc[4 rows][8 folds] += W[4][128 k] * X[128 k][8 folds].
 // wimg: item image [4][32 lanes] float4, element i of lane l = W[row][kbase + l + 32 i].
 // xs: exchanged vector in shared memory at row kbase (a multiple of 128); lane l consumes k = kbase + l + 32 i.
@@ -269,11 +242,21 @@ struct Ctx {
     int tid, lane, warp, cta;
     int cond_visit;      // running count of conditioning visits (selects staging buffer / parity)
     long long tprev;     // profiling: last timestamp (thread 0)
+    int pf_pending;      // a TMA prefetch of the next gather is in flight (CTA-uniform)
+    unsigned pf_parity;  // phase parity of the prefetch mbarrier
+    float du[3], dfx;    // draws fetched by draws_issue, waiting for draws_commit (warp 9)
+    // LL gather: this thread owns the 16-byte chunks i = tid + 512 j (unit/class k = i/4, folds 2(i%4), +1);
+    // their shared-memory destinations are affine in j, so the offsets are computed once.
+    int gv0;             // exchanged-vector layout: stage offset of chunk j = 0 (chunk j adds 1024 j)
+    int gl0, gl1, glj;   // fold-major logits image: offsets of the two folds of chunk 0, stride per chunk
 };
-// profiling tick: charge the cycles since the previous tick to `slot` (thread 0 of the CTA only)
+// profiling tick: charge the cycles since the previous tick to `slot` (thread 0 of the CTA only).
+// Compiled out of the production kernel (PROF = false): the tick sites alone were ~5 KiB of code
+// and the step loop has to fit the instruction cache.
+template <bool PROF>
 __device__ __forceinline__ void tick(Ctx &c, int slot)
 {
-    if (c.p->prof && c.tid == 0) {
+    if (PROF && c.tid == 0) {
         const long long now = clock64();
         reinterpret_cast<long long *>(c.sm + c.m.samp + 768)[slot] += now - c.tprev;
         c.tprev = now;
@@ -287,17 +270,155 @@ __device__ __forceinline__ unsigned long long *xb_base(const Ctx &c, int g)
     return c.p->xb + (size_t)g * xb_group(c.p->rows5 * c.p->nprod5);
 }
 
-// LL-gather one exchanged vector of group g into the staging buffer; CTA-uniform result
-// (false = watchdog fired somewhere in this CTA; the kernel then exits and the host reports it).
-__device__ __forceinline__ bool cta_gather(Ctx &c, const unsigned long long *src, int npairs, unsigned epoch, int npl = 0)
+// LL gather of one exchanged vector (npairs {value, epoch} pairs) into the staging buffer.
+// Every thread loads its (up to 4 per batch) 16-byte chunks -- from the TMA-prefetched copy in
+// shared memory when there is one, else from L2 -- and re-polls L2 until both epochs of every
+// chunk match (all stale chunks are re-read together).  `logits` selects the fold-major image
+// consumed by the RAW sampler.  CTA-uniform result: false = the watchdog fired somewhere in
+// this CTA (the kernel then exits and the host reports WRNN_ERR_TIMEOUT).
+template <bool PROF>
+__device__ __forceinline__ bool cta_gather_direct(Ctx &c, const unsigned long long *src, int npairs, unsigned epoch, bool logits,
+                                                  const float *raw = nullptr)
 {
     int *abort_flag = reinterpret_cast<int *>(c.sm + c.m.mbar + 6);
-    if (!gather_ll(c.sm + c.m.stage, src, npairs, epoch, c.tid, npl)) {
-        *abort_flag = 1;
-        atomicExch(c.p->status, -4);
+    float *dst = c.sm + c.m.stage;
+    if (npairs == VEC) {
+        // the common case: exactly 4 chunks per thread, no bounds checks
+        uint4 v[4];
+        const unsigned long long *gp = src + 2 * c.tid;
+        if (raw) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4 *>(raw + 4 * (c.tid + j * NTHREADS));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = ld_pairs2(gp + 2 * j * NTHREADS);
+        }
+        for (int spin = 0;; ++spin) {
+            const bool b0 = (v[0].y != epoch) | (v[0].w != epoch), b1 = (v[1].y != epoch) | (v[1].w != epoch),
+                       b2 = (v[2].y != epoch) | (v[2].w != epoch), b3 = (v[3].y != epoch) | (v[3].w != epoch);
+            if (!(b0 | b1 | b2 | b3)) break;
+            if (spin > POLL_CAP) {
+                *abort_flag = 1;
+                atomicExch(c.p->status, -4);
+                break;
+            }
+            if (PROF && c.tid == 0) reinterpret_cast<long long *>(c.sm + c.m.samp + 768)[raw ? 17 : 18] += 1;
+            if (b0) v[0] = ld_pairs2(gp);
+            if (b1) v[1] = ld_pairs2(gp + 2 * NTHREADS);
+            if (b2) v[2] = ld_pairs2(gp + 4 * NTHREADS);
+            if (b3) v[3] = ld_pairs2(gp + 6 * NTHREADS);
+        }
+        if (!logits) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float2 *>(dst + c.gv0 + j * 1024) = make_float2(__uint_as_float(v[j].x), __uint_as_float(v[j].z));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                dst[c.gl0 + j * c.glj] = __uint_as_float(v[j].x);
+                dst[c.gl1 + j * c.glj] = __uint_as_float(v[j].z);
+            }
+        }
+    } else {
+        // any other size (MOL logits, RAW with C != 512): one chunk at a time
+        const int nchunks = npairs >> 1;
+#pragma unroll 1
+        for (int i = c.tid, j = 0; i < nchunks; i += NTHREADS, ++j) {
+            uint4 v = raw ? *reinterpret_cast<const uint4 *>(raw + 4 * i) : ld_pairs2(src + 2 * i);
+            for (int spin = 0; v.y != epoch || v.w != epoch; ++spin) {
+                if (spin > POLL_CAP) {
+                    *abort_flag = 1;
+                    atomicExch(c.p->status, -4);
+                    break;
+                }
+                v = ld_pairs2(src + 2 * i);
+            }
+            if (!logits) *reinterpret_cast<float2 *>(dst + c.gv0 + j * 1024) = make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
+            else {
+                dst[c.gl0 + j * c.glj] = __uint_as_float(v.x);
+                dst[c.gl1 + j * c.glj] = __uint_as_float(v.z);
+            }
+        }
     }
+    tick<PROF>(c, 19);                           // own chunks validated + scattered
     __syncthreads();
+    tick<PROF>(c, 20);                           // waiting for the other warps at the barrier
     return *abort_flag == 0;
+}
+
+// The static visit order: for step t, stage 0 (SA) .. 4 (S5), groups 0..G-1 inside each stage.
+// Advance (t, stage, g) to the next visit that gathers a vector; false when there is none.
+__device__ __forceinline__ bool next_gather_visit(const KParams &p, int cta, int &t, int &stage, int &g)
+{
+    const int nst = cta < p.nprod5 ? 5 : 4;
+    for (;;) {
+        if (++g >= p.G) {
+            g = 0;
+            if (++stage >= nst) {
+                stage = 0;
+                ++t;
+            }
+        }
+        if (t > p.S) return false;
+        if (stage == 0) {
+            if (t > 0) return true;              // SA of step t samples the logits of step t-1
+        } else if (t < p.S)
+            return true;
+        else
+            return false;
+    }
+}
+__device__ __forceinline__ void visit_source(Ctx &c, int t, int stage, int g, const unsigned long long *&src, int &npairs, unsigned &epoch, bool &logits)
+{
+    const KParams &p = *c.p;
+    const unsigned long long *xb = xb_base(c, g);
+    if (stage == 0) {
+        src = xb + XB_LG;
+        npairs = p.rows5 * p.nprod5 * BT;
+        epoch = (unsigned)t;
+        logits = p.mode == 0;                   // RAW: fold-major image for the sampler; MOL: vector layout
+    } else {
+        src = xb + (stage - 1) * VEC;            // H1 | H2 | Y1 | Y2
+        npairs = VEC;
+        epoch = (unsigned)t + 1u;
+        logits = false;
+    }
+}
+
+// Gather the vector of visit (t, stage, g).  When a TMA prefetch of it was issued during the
+// previous visit, the pairs are taken from shared memory (stale ones -- a producer that had not
+// published yet -- are re-polled from L2); afterwards the NEXT visit's vector is prefetched with
+// one cp.async.bulk so its L2 latency overlaps this visit's mat-vecs.  With a single group the
+// next vector does not exist yet, so the prefetch is only used for G > 1.
+template <bool PROF>
+__device__ __forceinline__ bool cta_gather(Ctx &c, int t, int stage, int g)
+{
+    const KParams &p = *c.p;
+    const unsigned long long *src;
+    int npairs;
+    bool logits;
+    unsigned epoch;
+    visit_source(c, t, stage, g, src, npairs, epoch, logits);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(c.sm + c.m.mbar + 8);
+    const float *raw = nullptr;
+    if (c.pf_pending) {
+        while (!mbar_try_wait(bar, c.pf_parity)) {
+        }
+        c.pf_parity ^= 1u;
+        raw = c.sm + c.m.raw;
+        tick<PROF>(c, 16);                             // time spent waiting for the prefetch to land
+    }
+    const bool ok = cta_gather_direct<PROF>(c, src, npairs, epoch, logits, raw);   // ends with __syncthreads: raw is free again
+    // every visit but the very last one (SA of step S, last group) is followed by another gather
+    c.pf_pending = (p.G > 1 && p.rows5 <= 4 && !(t == p.S && g == p.G - 1)) ? 1 : 0;
+    if (c.pf_pending && c.tid == 0) {
+        int nt = t, ns = stage, ng = g;
+        next_gather_visit(p, c.cta, nt, ns, ng);
+        visit_source(c, nt, ns, ng, src, npairs, epoch, logits);
+        mbar_expect_tx(bar, (unsigned)npairs * 8u);
+        tma_bulk_g2s(c.sm + c.m.raw, src, (unsigned)npairs * 8u, bar);
+    }
+    return ok;
 }
 
 // Issue the TMA row copies of the conditioning for conditioning-visit v (group v % G, step v / G)
@@ -316,9 +437,9 @@ __device__ __forceinline__ void cond_issue(Ctx &c, int v)
     bool valid = false;
     long long row = 0;
     if (f < p.group_nf[g]) {
-        const int b = p.group_fold0[g] + f;
-        row = p.fold_start[b] + step;
-        valid = row < p.fold_limit[b];
+        const long long *fs = reinterpret_cast<const long long *>(c.sm + c.m.samp);   // [MAXG*8] starts | [MAXG*8] limits
+        row = fs[g * BT + f] + step;
+        valid = row < fs[MAXG * BT + g * BT + f];
     }
     const unsigned m = __ballot_sync(0xffffffffu, valid);
     if (c.lane == 0) {
@@ -369,31 +490,47 @@ __device__ __forceinline__ void cond_finalize(Ctx &c, int g, int w)
 }
 
 // Fetch the uniforms / forced value that step `step` of group g will need at sampling time.
-__device__ __forceinline__ void prefetch_draws(Ctx &c, int g, int step)
+// Two-phase so the global-load latency (injected uniforms) overlaps the gather + sampling of the
+// visit instead of making this warp late at the next block barrier: issue early, commit later.
+__device__ __forceinline__ void draws_issue(Ctx &c, int g, int step)
 {
     const KParams &p = *c.p;
-    float *pg = priv(c, g);
     const int nu = p.n_u;
-    for (int i = c.lane; i < BT * nu; i += 32) {
-        const int f = i / nu, j = i - f * nu;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int i = c.lane + 32 * q;
         float u = 0.f;
-        if (f < p.group_nf[g]) {
-            const int b = p.group_fold0[g] + f;
-            if (p.uniforms) u = p.uniforms[((size_t)step * p.B + b) * nu + j];
-            else {
-                uint4 r = philox4x32_10(make_uint4((unsigned)step, (unsigned)b, (unsigned)(j >> 2), 0u),
-                                        make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
-                const unsigned x = ((j & 3) == 0) ? r.x : ((j & 3) == 1) ? r.y : ((j & 3) == 2) ? r.z : r.w;
-                u = u01(x);
+        if (i < BT * nu) {
+            const int f = i / nu, j = i - f * nu;
+            if (f < p.group_nf[g]) {
+                const int b = p.group_fold0[g] + f;
+                if (p.uniforms) u = p.uniforms[((size_t)step * p.B + b) * nu + j];
+                else {
+                    uint4 r = philox4x32_10(make_uint4((unsigned)step, (unsigned)b, (unsigned)(j >> 2), 0u),
+                                            make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
+                    const unsigned x = ((j & 3) == 0) ? r.x : ((j & 3) == 1) ? r.y : ((j & 3) == 2) ? r.z : r.w;
+                    u = u01(x);
+                }
             }
         }
-        pg[PG_U + f * 11 + j] = u;
+        c.du[q] = u;
     }
-    if (c.lane < BT) {
-        float fx = 0.f;
-        if (p.forced_x && c.lane < p.group_nf[g]) fx = p.forced_x[(size_t)step * p.B + p.group_fold0[g] + c.lane];
-        pg[PG_FX + c.lane] = fx;
+    c.dfx = 0.f;
+    if (p.forced_x && c.lane < p.group_nf[g]) c.dfx = p.forced_x[(size_t)step * p.B + p.group_fold0[g] + c.lane];
+}
+__device__ __forceinline__ void draws_commit(Ctx &c, int g)
+{
+    float *pg = priv(c, g);
+    const int nu = c.p->n_u;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        const int i = c.lane + 32 * q;
+        if (i < BT * nu) {
+            const int f = i / nu, j = i - f * nu;
+            pg[PG_U + f * 11 + j] = c.du[q];
+        }
     }
+    if (c.lane < BT) pg[PG_FX + c.lane] = c.dfx;
 }
 
 // ---- sampling: logits of step s are in c.sm[stage]; writes the fed-back x into priv ----------
@@ -556,7 +693,8 @@ __device__ __forceinline__ void build_work_table(Ctx &c)
     reinterpret_cast<int4 *>(c.sm + c.m.tab)[c.tid] = e;
 }
 
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel(const KParams prm)
+template <bool PROF>
+__device__ __forceinline__ void persistent_body(const KParams &prm)
 {
     extern __shared__ __align__(128) float sm[];
     Ctx c;
@@ -569,11 +707,21 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
     c.cta = blockIdx.x;
     c.cond_visit = 0;
     c.tprev = 0;
+    c.pf_pending = 0;
+    c.pf_parity = 0;
+    {   // scatter offsets of this thread's gather chunks (see Ctx)
+        const int k0 = c.tid >> 2, f0 = (c.tid & 3) * 2;
+        c.gv0 = xidx(k0, f0);
+        const int npl = prm.mode == 0 ? prm.C >> 5 : 32;
+        c.gl0 = lg_idx(npl, k0, f0);
+        c.gl1 = lg_idx(npl, k0, f0 + 1);
+        c.glj = (128 / npl) * (npl + 4);
+    }
     const KParams &p = prm;
     const int G = p.G, S = p.S;
     const int lane = c.lane, w = c.warp;
 
-    // ---- prologue: resident weights, zero state, conditioning projections of step 0 ----------
+    // ---- prologue: resident weights, zero state ------------------------------------------------
     {
         const float4 *src = reinterpret_cast<const float4 *>(p.wimg + (size_t)c.cta * w_total(p.rows5));
         float4 *dst = reinterpret_cast<float4 *>(sm + c.m.w);
@@ -581,13 +729,22 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
         for (int i = c.tid; i < CONDK * BT; i += NTHREADS) sm[c.m.cx + i] = 0.f;
         for (int i = c.tid; i < MAXG * PG_SIZE; i += NTHREADS) sm[c.m.priv + i] = 0.f;
         build_work_table(c);
+        if (c.tid < MAXG * BT) {                 // fold row ranges cached in shared memory (cond_issue reads them every visit)
+            const int g = c.tid / BT, f = c.tid % BT;
+            long long *fs = reinterpret_cast<long long *>(sm + c.m.samp);
+            const bool live = g < p.G && f < p.group_nf[g];
+            fs[c.tid] = live ? p.fold_start[p.group_fold0[g] + f] : 0;
+            fs[MAXG * BT + c.tid] = live ? p.fold_limit[p.group_fold0[g] + f] : 0;
+        }
         if (c.tid == 0) {
             uint64_t *bar = reinterpret_cast<uint64_t *>(sm + c.m.mbar);
             mbar_init(bar, 1);
             mbar_init(bar + 1, 1);
+            mbar_init(bar + 4, 1);               // prefetch barrier (floats [8,9] of the mbar block)
             *reinterpret_cast<int *>(sm + c.m.mbar + 6) = 0;
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
+        if (c.tid < 2 * PROF_SLOTS) sm[c.m.samp + 768 + c.tid] = 0.f;
         __syncthreads();
         const float *sv = small(c);
         for (int g = 0; g < G; ++g) {           // h = 0  =>  gh = b_hh  (fatchord_version.py:173-174)
@@ -597,36 +754,38 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
                 pg[PG_GH2 + c.tid] = sv[SV_BHH2 + (c.tid >> 3)];
             }
         }
-        if (c.tid < 2 * PROF_SLOTS) sm[c.m.samp + 768 + c.tid] = 0.f;
-        if (c.warp == NWARPS - 1) cond_issue(c, 0);
-        __syncthreads();
-        for (int g = 0; g < G; ++g) {
-            cond_visit(c);
-            run_items(c, 2, w >= 4);
-            __syncthreads();
-            cond_finalize(c, g, w);
-            if (w == 9) prefetch_draws(c, g, 0);
-        }
-        __syncthreads();
     }
 
-    if (p.prof && c.tid == 0) c.tprev = clock64();
-    const int cpairs = p.rows5 * p.nprod5 * BT;
-    for (int t = 0; t <= S; ++t) {
+    if (PROF && c.tid == 0) c.tprev = clock64();
+    // t = -1 is the warm-up pass: only the conditioning half of stage 3 runs (projections of step 0),
+    // so every helper below has exactly ONE call site -- the step loop must fit the instruction cache.
+    for (int t = -1; t <= S; ++t) {
         const unsigned epoch = (unsigned)t + 1u;
         // stage 0 = SA (sample step t-1, GRU1 of step t); 1..4 = S2..S5.  Groups are visited in a
         // static order inside each stage so one group's exchange overlaps the others' mat-vecs.
-        for (int stage = 0; stage < 5; ++stage) {
+        for (int stage = (t < 0 ? 3 : 0); stage < (t < 0 ? 4 : 5); ++stage) {
             if (stage == 4 && c.cta >= p.nprod5) break;            // only the logits producers run S5
+            if (stage > 0 && t == S) break;
             for (int g = 0; g < G; ++g) {
                 float *pg = priv(c, g);
                 unsigned long long *xb = xb_base(c, g);
                 const float *sv = small(c);
                 const float *part = sm + c.m.part;
+                const bool warm = t < 0;
+                if (stage == 3) {
+                    if (t == -1 && g == 0 && w == NWARPS - 1) cond_issue(c, 0);
+                    if (t == -1 && g == 0) __syncthreads();
+                    cond_visit(c);               // stages cond(t+1) of this group, prefetches the next visit
+                    tick<PROF>(c, 9);
+                    if (w == 9 && !warm) draws_issue(c, g, t);     // draws consumed by the sample of step t (at SA of t+1)
+                }
+                if (!warm && (stage > 0 || t > 0)) {
+                    if (!cta_gather<PROF>(c, t, stage, g)) return;  // LG (t-1) | H1 | H2 | Y1 | Y2
+                    tick<PROF>(c, 3 * stage + (stage >= 3 ? 1 : 0));
+                }
                 if (stage == 0) {
                     if (t > 0) {
-                        if (!cta_gather(c, xb + XB_LG, cpairs, (unsigned)t, p.mode == 0 ? p.C >> 5 : 0)) return;
-                        tick(c, 0);
+                        dump_logits(c, g, t - 1);
                         if (p.mode != 0) sample_mol(c, g, t - 1);
                         else switch (p.C) {
                             case 1024: sample_raw<32>(c, g, t - 1); break;
@@ -635,59 +794,43 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
                             case 128: sample_raw<4>(c, g, t - 1); break;
                             default: sample_raw<2>(c, g, t - 1); break;
                         }
-                        dump_logits(c, g, t - 1);
                         __syncthreads();
-                        tick(c, 1);
-                        if (w == 9 && t < S) prefetch_draws(c, g, t);   // draws for the sample of step t
+                        tick<PROF>(c, 1);
                     }
-                    if (t < S && w == 0) {
-                        // rnn1 GRU cell for this CTA's 4 units x 8 folds (torch gate order r, z, n)
-                        const int u = lane >> 3, f = lane & 7;
-                        const float x = pg[PG_X + f];
-                        const float gr = pg[PG_P1 + lane] + x * sv[SV_U1 + u] + sv[SV_B1 + u];
-                        const float gz = pg[PG_P1 + 32 + lane] + x * sv[SV_U1 + 4 + u] + sv[SV_B1 + 4 + u];
-                        const float gn = pg[PG_P1 + 64 + lane] + x * sv[SV_U1 + 8 + u] + sv[SV_B1 + 8 + u];
-                        const float r = sigmoidf_(gr + pg[PG_GH1 + lane]);
-                        const float z = sigmoidf_(gz + pg[PG_GH1 + 32 + lane]);
-                        const float n = tanhf(gn + r * pg[PG_GH1 + 64 + lane]);
-                        const float h = (1.0f - z) * n + z * pg[PG_H1 + lane];
-                        pg[PG_H1 + lane] = h;
-                        publish_line(xb + XB_H1, c.cta, lane, h, epoch);
-                        tick(c, 2);
-                    }
-                    continue;
+                    if (t == S) continue;
+                } else {
+                    run_items(c, stage - 1, !warm ? (stage != 3 || w < 4 || t + 1 < S) : (w >= 4));
+                    __syncthreads();
+                    tick<PROF>(c, 3 * stage + 1 + (stage >= 3 ? 1 : 0));
                 }
-                if (t == S) break;
-                if (stage == 3) {
-                    cond_visit(c);               // stages cond(t+1) of this group, prefetches the next visit
-                    tick(c, 9);
-                }
-                if (!cta_gather(c, xb + (stage - 1) * VEC, VEC, epoch)) return;      // H1 | H2 | Y1 | Y2
-                tick(c, 3 * stage + (stage == 3 ? 1 : 0) + (stage == 4 ? 1 : 0));
-                run_items(c, stage - 1, stage != 3 || w < 4 || t + 1 < S);
-                __syncthreads();
-                tick(c, 3 * stage + 1 + (stage == 3 ? 1 : 0) + (stage == 4 ? 1 : 0));
-                if (stage == 1) {
-                    // S2: rnn2 cell; gh1 of the next step; Wfc1x . h1
+                // ---- finalize: pointwise math of this CTA's 4 units x 8 folds, publish --------------
+                if (stage <= 1) {
                     if (w == 0) {
+                        // GRU cell (torch gate order r, z, n): stage 0 = rnn1 (input side folded into P1),
+                        // stage 1 = rnn2 (input side = Wih2x . h1 from the items + P2)
                         const int u = lane >> 3, f = lane & 7;
                         const float x = pg[PG_X + f];
+                        const int P = stage == 0 ? PG_P1 : PG_P2, GH = stage == 0 ? PG_GH1 : PG_GH2, H = stage == 0 ? PG_H1 : PG_H2;
+                        const int SU = stage == 0 ? SV_U1 : SV_U2, SB = stage == 0 ? SV_B1 : SV_B2;
                         float gi[3];
 #pragma unroll
-                        for (int q = 0; q < 3; ++q)
-                            gi[q] = (part[q * 32 + lane] + part[(7 + q) * 32 + lane]) + pg[PG_P2 + q * 32 + lane] + x * sv[SV_U2 + q * 4 + u] + sv[SV_B2 + q * 4 + u];
-                        const float r = sigmoidf_(gi[0] + pg[PG_GH2 + lane]);
-                        const float z = sigmoidf_(gi[1] + pg[PG_GH2 + 32 + lane]);
-                        const float n = tanhf(gi[2] + r * pg[PG_GH2 + 64 + lane]);
-                        const float h2 = (1.0f - z) * n + z * pg[PG_H2 + lane];
-                        pg[PG_H2 + lane] = h2;
-                        publish_line(xb + XB_H2, c.cta, lane, h2, epoch);
-                        tick(c, 5);
-                    } else if (w <= 3) {
-                        const int q = w - 1;     // gh1 of the NEXT step: Whh1 . h1_t + b_hh1
-                        pg[PG_GH1 + q * 32 + lane] = (part[(3 + q) * 32 + lane] + part[(10 + q) * 32 + lane]) + sv[SV_BHH1 + q * 4 + (lane >> 3)];
-                    } else if (w == 4) {
-                        pg[PG_F1 + lane] = part[6 * 32 + lane] + part[13 * 32 + lane];      // Wfc1x . h1_t
+                        for (int q = 0; q < 3; ++q) {
+                            gi[q] = pg[P + q * 32 + lane] + x * sv[SU + q * 4 + u] + sv[SB + q * 4 + u];
+                            if (stage == 1) gi[q] += part[q * 32 + lane] + part[(7 + q) * 32 + lane];
+                        }
+                        const float r = sigmoidf_(gi[0] + pg[GH + lane]);
+                        const float z = sigmoidf_(gi[1] + pg[GH + 32 + lane]);
+                        const float n = tanhf(gi[2] + r * pg[GH + 64 + lane]);
+                        const float h = (1.0f - z) * n + z * pg[H + lane];
+                        pg[H + lane] = h;
+                        publish_line(xb + (stage == 0 ? XB_H1 : XB_H2), c.cta, lane, h, epoch);
+                        tick<PROF>(c, stage == 0 ? 2 : 5);
+                    } else if (stage == 1) {
+                        if (w <= 3) {
+                            const int q = w - 1; // gh1 of the NEXT step: Whh1 . h1_t + b_hh1
+                            pg[PG_GH1 + q * 32 + lane] = (part[(3 + q) * 32 + lane] + part[(10 + q) * 32 + lane]) + sv[SV_BHH1 + q * 4 + (lane >> 3)];
+                        } else if (w == 4)
+                            pg[PG_F1 + lane] = part[6 * 32 + lane] + part[13 * 32 + lane];      // Wfc1x . h1_t
                     }
                 } else if (stage == 2) {
                     // S3: fc1 (h2 part + saved h1 part); gh2 of the next step
@@ -696,24 +839,25 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
                         float y = (((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + pg[PG_F1 + lane]) + pg[PG_P3 + lane] + pg[PG_X + f] * sv[SV_U3 + u] + sv[SV_B3 + u];
                         y = fmaxf(y, 0.f);
                         publish_line(xb + XB_Y1, c.cta, lane, y, epoch);
-                        tick(c, 8);
+                        tick<PROF>(c, 8);
                     } else if (w <= 3) {
                         const int q = w - 1, s0 = 4 + q;
                         pg[PG_GH2 + q * 32 + lane] = ((part[s0 * 32 + lane] + part[(s0 + 3) * 32 + lane]) + (part[(s0 + 6) * 32 + lane] + part[(s0 + 9) * 32 + lane])) + sv[SV_BHH2 + q * 4 + (lane >> 3)];
                     }
                 } else if (stage == 3) {
-                    // S4: fc2; conditioning projections of step t+1
-                    if (w == 0) {
+                    // S4: fc2; conditioning projections of step t+1; draws of step t
+                    if (w == 0 && !warm) {
                         float y = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + pg[PG_P4 + lane] + sv[SV_B4 + (lane >> 3)];
                         y = fmaxf(y, 0.f);
                         publish_line(xb + XB_Y2, c.cta, lane, y, epoch);
-                        tick(c, 12);
+                        tick<PROF>(c, 12);
                     }
                     __syncwarp();
                     if (t + 1 < S) {
                         if (w == 0) pg[PG_P4 + lane] = part[(4 + 11) * 32 + lane];
                         else if (w != 8) cond_finalize(c, g, w);
                     }
+                    if (w == 9 && !warm) draws_commit(c, g);
                 } else {
                     // S5: logits of this CTA's rows5 classes
                     if (w * 4 < p.rows5) {
@@ -722,14 +866,18 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_ker
                         const int k = p.rows5 * c.cta + w * 4 + (lane >> 3);
                         st_pair(xb + XB_LG + k * BT + (lane & 7), v, epoch);
                     }
-                    tick(c, 15);
+                    tick<PROF>(c, 15);
                 }
             }
         }
     }
-    if (p.prof && c.tid == 0)
+    if (PROF && p.prof && c.tid == 0)
         for (int i = 0; i < PROF_SLOTS; ++i) p.prof[(size_t)c.cta * PROF_SLOTS + i] = reinterpret_cast<long long *>(sm + c.m.samp + 768)[i];
 }
+
+extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel(const KParams prm) { persistent_body<false>(prm); }
+// same kernel with the per-stage clock64 accounting compiled in (wrnn_set_profiling)
+extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel_prof(const KParams prm) { persistent_body<true>(prm); }
 
 // Exchange microbenchmark: the same publish / LL-gather sequence on an otherwise empty kernel.
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe_kernel(const KParams prm)
@@ -743,6 +891,8 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe
     c.lane = c.tid & 31;
     c.warp = c.tid >> 5;
     c.cta = blockIdx.x;
+    c.gv0 = xidx(c.tid >> 2, (c.tid & 3) * 2);
+    c.gl0 = c.gl1 = c.glj = 0;
     if (c.tid == 0) *reinterpret_cast<int *>(sm + c.m.mbar + 6) = 0;
     __syncthreads();
     unsigned long long *xb = xb_base(c, 0);
@@ -751,7 +901,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe
         unsigned long long *vec = xb + (it & 3) * VEC;
         const unsigned epoch = (unsigned)it + 1u;
         if (c.warp == 0) publish_line(vec, c.cta, c.lane, acc + (float)it, epoch);
-        if (!cta_gather(c, vec, VEC, epoch)) return;
+        if (!cta_gather_direct<false>(c, vec, VEC, epoch, false)) return;
         acc += sm[c.m.stage + c.tid] * 1e-30f;
         __syncthreads();
     }

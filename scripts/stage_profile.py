@@ -12,7 +12,8 @@ from oracle import synth  # noqa: E402
 
 SLOTS = ["SA gather(logits)", "SA sample", "SA gru1+publish", "S2 gather(h1)", "S2 items", "S2 finalize",
          "S3 gather(h2)", "S3 items", "S3 finalize", "S4 cond_visit", "S4 gather(y1)", "S4 items", "S4 finalize",
-         "S5 gather(y2)", "S5 items", "S5 finalize"]
+         "S5 gather(y2)", "S5 items", "S5 finalize", "prefetch mbar wait", "re-polls after prefetch (thread 0, count)",
+         "re-polls direct (thread 0, count)", "gather: own chunks", "gather: barrier wait"]
 
 
 def main():
@@ -23,7 +24,7 @@ def main():
     m.cuda()
     eng = m._engine(dev)
     S = 3000
-    for B in (8, 14, 20, 64):
+    for B in (8, 20):
         L = S + 64
         mu = torch.rand(B * L, 80, device=dev)
         au = torch.randn(B * L, 128, device=dev)
