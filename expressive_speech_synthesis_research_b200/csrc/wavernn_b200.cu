@@ -501,22 +501,26 @@ static void np_linspace(double start, double stop, int64_t num, double *y)
 }
 
 // One thread per output sample.  fatchord_version.py:222-237 + utility/dsp.py:100-105.
+// Rows of `samples` are the global folds [fold0, fold0 + B); out[i] is global position seg_start + i.
+// A fold outside the given rows contributes nothing (the multi-GPU caller passes the neighbour's
+// overlap samples as an extra row, expressive_speech_synthesis_research_b200/distributed.py).
 __global__ void xfade_unfold_kernel(const float *__restrict__ samples, int B, int S, int batched, int overlap,
                                     const double *__restrict__ fade_in, const double *__restrict__ fade_out,
                                     const double *__restrict__ tail, int mu_classes, long long wave_len, int tail_len,
-                                    double *__restrict__ out)
+                                    long long fold0, long long seg_start, long long seg_len, double *__restrict__ out)
 {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= wave_len) return;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= seg_len) return;
+    const long long p = seg_start + idx;
     double v;
     if (batched) {
         const long long hop = (long long)S - overlap;            // target + overlap
-        long long hi = p / hop;
-        if (hi > B - 1) hi = B - 1;
+        const long long hi = p / hop;
         v = 0.0;                                                  // np.zeros(total_len), :375
-        for (long long i = hi - 1; i <= hi; ++i) {                // ascending fold order, :378-381
-            if (i < 0) continue;
-            const long long s = p - i * hop;
+        for (long long gi = hi - 1; gi <= hi; ++gi) {             // ascending fold order, :378-381
+            const long long i = gi - fold0;
+            if (i < 0 || i >= B) continue;
+            const long long s = p - gi * hop;
             if (s < 0 || s >= S) continue;
             double y = (double)samples[i * S + s];                // .astype(np.float64), :224
             if (s < overlap) y = __dmul_rn(y, fade_in[s]);        // :372
@@ -533,15 +537,15 @@ __global__ void xfade_unfold_kernel(const float *__restrict__ samples, int B, in
         v = __dmul_rn(q, __dsub_rn(pw, 1.0));
     }
     if (p >= wave_len - tail_len) v = __dmul_rn(v, tail[p - (wave_len - tail_len)]);   // :235-237
-    out[p] = v;
+    out[idx] = v;
 }
 
 static thread_local double *t_tables_dev = nullptr;
 static thread_local int t_overlap = -1, t_tail = -1, t_device = -1;
 
-extern "C" int32_t wrnn_xfade_unfold(const float *samples, int32_t num_folds, int32_t steps,
-                                     int32_t batched, int32_t overlap, int32_t mu_law_classes,
-                                     int64_t wave_len, int32_t tail_fade, double *out, void *stream)
+static int32_t xfade_impl(const float *samples, int32_t num_folds, int32_t steps, int32_t batched, int32_t overlap,
+                          int32_t mu_law_classes, int64_t wave_len, int32_t tail_fade, int64_t fold0, int64_t total_folds,
+                          int64_t seg_start, int64_t seg_len, double *out, void *stream)
 {
     if (!samples || !out) return fail(WRNN_ERR_INVALID, "null pointer argument");
     if (num_folds <= 0 || steps <= 0 || wave_len <= 0) return fail(WRNN_ERR_INVALID, "num_folds, steps and wave_len must be positive");
@@ -551,13 +555,16 @@ extern "C" int32_t wrnn_xfade_unfold(const float *samples, int32_t num_folds, in
     if (batched) {
         if (overlap <= 0) return fail(WRNN_ERR_INVALID, "batched crossfade needs overlap > 0 (reference: y[:, -0:] broadcast error)");
         if (steps < 2 * overlap) return fail(WRNN_ERR_INVALID, "steps (%d) < 2 * overlap (%d)", steps, overlap);
-        total = (int64_t)num_folds * (steps - overlap) + overlap;
+        total = total_folds * (steps - overlap) + overlap;
     } else {
         if (num_folds != 1) return fail(WRNN_ERR_INVALID, "unbatched epilogue takes exactly one fold");
         total = steps;
         overlap = 0;
     }
     if (wave_len > total) return fail(WRNN_ERR_INVALID, "wave_len %lld exceeds the unfolded length %lld", (long long)wave_len, (long long)total);
+    if (seg_start < 0 || seg_len <= 0 || seg_start + seg_len > wave_len)
+        return fail(WRNN_ERR_INVALID, "segment [%lld, +%lld) outside [0, wave_len %lld)", (long long)seg_start, (long long)seg_len, (long long)wave_len);
+    if (fold0 < 0 || fold0 + num_folds > total_folds) return fail(WRNN_ERR_INVALID, "fold rows [%lld, +%d) outside [0, %lld)", (long long)fold0, num_folds, (long long)total_folds);
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     cudaStream_t st = (cudaStream_t)stream;
@@ -582,11 +589,26 @@ extern "C" int32_t wrnn_xfade_unfold(const float *samples, int32_t num_folds, in
         t_device = dev;
     }
     const int threads = 256;
-    const long long blocks = (wave_len + threads - 1) / threads;
+    const long long blocks = (seg_len + threads - 1) / threads;
     xfade_unfold_kernel<<<(unsigned)blocks, threads, 0, st>>>(samples, num_folds, steps, batched, overlap, t_tables_dev,
                                                               t_tables_dev + overlap, t_tables_dev + 2 * overlap,
-                                                              mu_law_classes, wave_len, tail_fade, out);
+                                                              mu_law_classes, wave_len, tail_fade, fold0, seg_start, seg_len, out);
     CUDA_TRY(cudaGetLastError());
     g_epilogue_launches += 1;
     return WRNN_OK;
+}
+
+extern "C" int32_t wrnn_xfade_unfold(const float *samples, int32_t num_folds, int32_t steps,
+                                     int32_t batched, int32_t overlap, int32_t mu_law_classes,
+                                     int64_t wave_len, int32_t tail_fade, double *out, void *stream)
+{
+    return xfade_impl(samples, num_folds, steps, batched, overlap, mu_law_classes, wave_len, tail_fade, 0, num_folds, 0, wave_len, out, stream);
+}
+
+extern "C" int32_t wrnn_xfade_unfold_segment(const float *samples, int32_t num_rows, int32_t steps, int32_t overlap,
+                                             int32_t mu_law_classes, int64_t wave_len, int32_t tail_fade,
+                                             int64_t first_fold, int64_t total_folds, int64_t seg_start, int64_t seg_len,
+                                             double *out, void *stream)
+{
+    return xfade_impl(samples, num_rows, steps, 1, overlap, mu_law_classes, wave_len, tail_fade, first_fold, total_folds, seg_start, seg_len, out, stream);
 }

@@ -1,0 +1,153 @@
+"""Multi-GPU sharding of the generation path: one process per GPU (torch.distributed, NCCL over
+NVLink on the GPU box, gloo in the CPU tests).
+
+Every fold is independent until the crossfade (zero initial state, fatchord_version.py:173-175),
+so the path shards without any collective inside the step loop:
+
+* sentence sets -- whole utterances go to ranks by longest-processing-time on their fold counts
+  (`plan_utterances`); no communication at all.
+* one long utterance -- contiguous fold ranges per rank (`fold_ranges`); after generation each
+  rank needs only the LAST `overlap` samples of its left neighbour's last fold to finish the
+  crossfade of its own span, so the single exchange is an all_gather of one [overlap] fp32 edge
+  per rank (2.2 KB at overlap=550).  Each rank then runs the segment epilogue
+  (wrnn_xfade_unfold_segment) on its span; concatenated spans are bit-identical to the
+  single-GPU waveform because every output sample is still (0 + a*fade_out) + b*fade_in in fp64.
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def plan_utterances(fold_counts, world_size):
+    """Longest-processing-time assignment of whole utterances to ranks.
+    Returns a list (per rank) of utterance indices; deterministic for equal counts."""
+    order = sorted(range(len(fold_counts)), key=lambda i: (-fold_counts[i], i))
+    load = [0] * world_size
+    plan = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        plan[r].append(i)
+        load[r] += fold_counts[i]
+    return plan
+
+
+def fold_ranges(num_folds, world_size):
+    """Contiguous fold ranges [lo, hi) per rank: rank g gets floor(g*B/G) .. floor((g+1)*B/G)."""
+    return [(g * num_folds // world_size, (g + 1) * num_folds // world_size) for g in range(world_size)]
+
+
+def exchange_edges(tail, group=None):
+    """all_gather of each rank's trailing-overlap edge ([overlap] fp32, zeros if the rank has no
+    folds).  Returns a [world, overlap] tensor on tail's device.  This is the only collective of
+    the sharded path."""
+    world = dist.get_world_size(group)
+    out = [torch.empty_like(tail) for _ in range(world)]
+    dist.all_gather(out, tail.contiguous(), group=group)
+    return torch.stack(out)
+
+
+def segment_rows(local_samples, left_tail, lo):
+    """Rows handed to the segment epilogue: the left neighbour's overlap samples as one extra
+    (otherwise zero) row in front of this rank's folds.  Returns (rows [n(+1), S], first_fold)."""
+    if lo == 0:
+        return local_samples, 0
+    ghost = torch.zeros_like(local_samples[:1])
+    ghost[0, -left_tail.numel():] = left_tail
+    return torch.cat([ghost, local_samples]), lo - 1
+
+
+def segment_bounds(lo, hi, num_folds, target, overlap, wave_len):
+    """Global sample range [start, stop) owned by the rank holding folds [lo, hi)."""
+    hop = target + overlap
+    start = lo * hop
+    stop = hi * hop + (overlap if hi == num_folds else 0)
+    return min(start, wave_len), min(stop, wave_len)
+
+
+def assemble_segment(rows, first_fold, num_folds, steps, overlap, mu_law_classes, wave_len, tail_fade, seg, unfold=None):
+    """Run the segment epilogue.  `unfold` lets the CPU tests substitute the oracle for the CUDA call."""
+    start, stop = seg
+    if stop <= start:
+        return torch.empty(0, dtype=torch.float64, device=rows.device)
+    if unfold is not None:
+        return unfold(rows, first_fold, num_folds, steps, overlap, mu_law_classes, wave_len, tail_fade, start, stop - start)
+    out = torch.empty(stop - start, dtype=torch.float64, device=rows.device)
+    stream = torch.cuda.current_stream(rows.device).cuda_stream
+    _lib.check(_lib.lib().wrnn_xfade_unfold_segment(rows.data_ptr(), rows.shape[0], steps, overlap, mu_law_classes, wave_len,
+                                                    tail_fade, first_fold, num_folds, start, stop - start, out.data_ptr(),
+                                                    ctypes.c_void_p(stream)))
+    return out
+
+
+def finish_sharded(local_samples, lo, hi, num_folds, target, overlap, mu_law_classes, wave_len, tail_fade,
+                   group=None, gather_to=0, unfold=None):
+    """Edge exchange + local crossfade/unfold + (optional) gather of the waveform spans.
+
+    local_samples: [hi-lo, S] fp32 samples of this rank's folds (may be empty).
+    Returns the full float64 waveform on rank `gather_to` (None elsewhere), or this rank's span
+    when gather_to is None."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    S = target + 2 * overlap
+    dev = local_samples.device
+    tail = local_samples[-1, S - overlap:].clone() if hi > lo else torch.zeros(overlap, dtype=torch.float32, device=dev)
+    edges = exchange_edges(tail, group)                       # the ONLY collective on the data path
+    ranges = fold_ranges(num_folds, world)
+    left = next((r for r in range(rank - 1, -1, -1) if ranges[r][1] > ranges[r][0]), None)
+    seg = segment_bounds(lo, hi, num_folds, target, overlap, wave_len)
+    if hi > lo:
+        rows, first = segment_rows(local_samples, edges[left] if left is not None else None, lo)
+        span = assemble_segment(rows, first, num_folds, S, overlap, mu_law_classes, wave_len, tail_fade, seg, unfold)
+    else:
+        span = torch.empty(0, dtype=torch.float64, device=dev)
+    if gather_to is None:
+        return span
+    sizes = [max(0, segment_bounds(a, b, num_folds, target, overlap, wave_len)[1]
+                 - segment_bounds(a, b, num_folds, target, overlap, wave_len)[0]) if b > a else 0 for a, b in ranges]
+    width = max(sizes + [1])
+    padded = torch.zeros(width, dtype=torch.float64, device=dev)
+    padded[:span.numel()] = span
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded, group=group)               # result assembly, not part of the step path
+    if rank != gather_to:
+        return None
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)])
+
+
+def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0, group=None, gather_to=0):
+    """One utterance, folds sharded over the ranks of `group`; equals
+    model.generate(mels, True, target, overlap, mu_law, uniforms=...) bit for bit.
+    `uniforms` is the full [S, B(,11)] tensor (each rank consumes its columns)."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mu_law = mu_law if model.mode == 'RAW' else False
+    model.eval()
+    try:
+        with torch.no_grad():
+            device = model._device()
+            eng = model._engine(device)
+            with torch.cuda.device(device):
+                mels = mels.to(device=device, dtype=torch.float32)
+                if model.upsample.resnet.conv_in.weight.device != device:
+                    model.to(device)
+                wave_len = (mels.size(-1) - 1) * model.hop_length
+                m_up, aux = model.conditioning(mels)
+                L = m_up.size(0)
+                B, _ = _lib.fold_index(L, target, overlap)
+                S = target + 2 * overlap
+                lo, hi = fold_ranges(B, world)[rank]
+                if hi > lo:
+                    starts = np.arange(lo, hi, dtype=np.int64) * (target + overlap)
+                    limits = np.full(hi - lo, L, dtype=np.int64)
+                    u = None if uniforms is None else torch.as_tensor(uniforms)[:, lo:hi]
+                    res = model._run_folds(eng, device, m_up, aux, starts, limits, S, u, seed + rank, None, False)
+                    local = res["samples"]
+                else:
+                    local = torch.empty(0, S, dtype=torch.float32, device=device)
+                wav = finish_sharded(local, lo, hi, B, target, overlap, model.n_classes if mu_law else 0, wave_len,
+                                     20 * model.hop_length, group=group, gather_to=gather_to)
+                return None if wav is None else wav.cpu().numpy()
+    finally:
+        model.train()

@@ -128,6 +128,19 @@ int32_t wrnn_xfade_unfold(const float *samples, int32_t num_folds, int32_t steps
                           int32_t batched, int32_t overlap, int32_t mu_law_classes,
                           int64_t wave_len, int32_t tail_fade, double *out, void *stream);
 
+/*
+ * The same epilogue for ONE SEGMENT of the waveform, used when the folds of an utterance are
+ * sharded over several GPUs (north star: "only the overlap samples are gathered"): `samples`
+ * holds rows for the global folds [first_fold, first_fold + num_rows) of a `total_folds`-fold
+ * utterance (a neighbour's overlap samples travel as one extra, otherwise zero, row), and
+ * out[i] receives global sample seg_start + i for i < seg_len.  Arithmetic per sample is the
+ * one of wrnn_xfade_unfold, so concatenated segments are bit-identical to the single-GPU result.
+ */
+int32_t wrnn_xfade_unfold_segment(const float *samples, int32_t num_rows, int32_t steps, int32_t overlap,
+                                  int32_t mu_law_classes, int64_t wave_len, int32_t tail_fade,
+                                  int64_t first_fold, int64_t total_folds, int64_t seg_start, int64_t seg_len,
+                                  double *out, void *stream);
+
 /* Introspection used by bench.py / tests. */
 typedef struct {
     int32_t ctas;                /* CTAs of the persistent kernel (one per SM) */
