@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -35,7 +36,8 @@ struct wrnn_handle {
     wrnn_config cfg;
     int device = 0, sm_count = 0;
     int rows5 = 4, nprod5 = 128, cpad = 512, n_u = 1;
-    int smem_bytes = 0;
+    int smem_bytes = 0, smem_limit = 0;   // dynamic shared memory of the last launch / opt-in limit of the device
+    int last_teams = 1;
     bool loaded = false;
     float *wimg = nullptr;
     unsigned long long *xb = nullptr;   // LL exchange buffers
@@ -125,8 +127,9 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
     h->nprod5 = nprod5;
     h->n_u = n_u;
     h->cpad = rows5 * nprod5;
-    h->smem_bytes = smem_map(rows5).total * (int)sizeof(float);
-    if ((size_t)h->smem_bytes > prop.sharedMemPerBlockOptin) {
+    h->smem_limit = (int)prop.sharedMemPerBlockOptin;
+    h->smem_bytes = smem_map(rows5, cfg->mode, cfg->n_classes, 1, 1).total * (int)sizeof(float);   // smallest configuration
+    if (h->smem_bytes > h->smem_limit) {
         const int need = h->smem_bytes;
         delete h;
         return fail(WRNN_ERR_CUDA, "kernel needs %d B shared memory, device allows %zu", need, prop.sharedMemPerBlockOptin);
@@ -137,9 +140,9 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
         wrnn_destroy(h);                                                             \
         return fail(WRNN_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e));          \
     }
-    H_TRY(cudaFuncSetAttribute(wavernn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-    H_TRY(cudaFuncSetAttribute(wavernn_exchange_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
-    H_TRY(cudaFuncSetAttribute(wavernn_persistent_kernel_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_bytes));
+    H_TRY(cudaFuncSetAttribute(wavernn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_limit));
+    H_TRY(cudaFuncSetAttribute(wavernn_exchange_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_limit));
+    H_TRY(cudaFuncSetAttribute(wavernn_persistent_kernel_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_limit));
     int occ = 0;
     H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wavernn_persistent_kernel, NTHREADS, h->smem_bytes));
     if (occ < 1) {
@@ -186,13 +189,15 @@ static void gemm_f64(const float *A, int lda, int M, int K, const std::vector<do
     }
 }
 
-// write one item image: rows r0..r0+3 (callback per row), columns kbase..kbase+127
+// write one item image: rows r0..r0+3 (callback per row), columns kbase..kbase+127.
+// Slot r of lane l holds row r ^ (l >> 3): the permutation that makes the kernel's butterfly
+// reduce-scatter select-free (wavernn_kernel.cuh, reduce_scatter32).
 template <class F>
 static void put_item(float *dst, int kbase, F rowval)
 {
     for (int r = 0; r < 4; ++r)
         for (int l = 0; l < 32; ++l)
-            for (int i = 0; i < 4; ++i) dst[(r * 32 + l) * 4 + i] = (float)rowval(r, kbase + l + 32 * i);
+            for (int i = 0; i < 4; ++i) dst[(r * 32 + l) * 4 + i] = (float)rowval(r ^ (l >> 3), kbase + l + 32 * i);
 }
 
 // Build the per-CTA shared-memory images (host, fp64 folding).  img: [NCTA][w_total(rows5)].
@@ -327,9 +332,38 @@ extern "C" int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w)
 }
 
 // ---- step loop launch --------------------------------------------------------------------------
+// Teams per CTA and conditioning buffers per team: as many teams as there are groups (at most MAXT)
+// and double-buffered staging when it fits the opt-in shared memory, else fewer.
+static void choose_teams(const wrnn_handle *h, int G, int &T, int &nbuf)
+{
+    for (T = G < MAXT ? G : MAXT; T >= 1; --T)
+        for (nbuf = 2; nbuf >= 1; --nbuf)
+            if (smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, T, nbuf).total * (int)sizeof(float) <= h->smem_limit) return;
+    T = 1;
+    nbuf = 1;
+}
+
 static int32_t launch_chunk(wrnn_handle *h, KParams &p, cudaStream_t st, bool probe)
 {
     void *args[] = {&p};
+    if (probe) {
+        p.T = 1;
+        p.nbuf = 1;
+    } else {
+        const char *force = getenv("WRNN_FORCE_TEAMS");          // development knob: cap the number of teams
+        choose_teams(h, p.G, p.T, p.nbuf);
+        if (force && atoi(force) >= 1 && atoi(force) < p.T) {
+            p.T = atoi(force);
+            p.nbuf = 2;
+            if (smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, p.T, 2).total * (int)sizeof(float) > h->smem_limit) p.nbuf = 1;
+        }
+    }
+    {
+        const char *sg = getenv("WRNN_STAGGER_CYCLES");     // development knob
+        p.stagger = sg ? atoi(sg) : 6000;
+    }
+    h->smem_bytes = smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, p.T, p.nbuf).total * (int)sizeof(float);
+    h->last_teams = p.T;
     // epochs restart at 1 every launch: clear stale {value, epoch} pairs of the previous one
     CUDA_TRY(cudaMemsetAsync(h->xb, 0, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));

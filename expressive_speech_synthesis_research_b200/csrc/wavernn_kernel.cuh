@@ -7,15 +7,19 @@
 //    (h1 | h2 | y1 | y2 | logits).  The exchange is flag-free ("LL" protocol): every value
 //    travels as an 8-byte {fp32 value, step epoch} pair written with one store; a consumer
 //    polls the pairs it needs until their epoch matches -- one L2 round trip, no fences, no
-//    contended flag lines (measured 1.4 us per 128-CTA all-gather vs 2.5-6.6 us with
-//    release/acquire flags; profiles/r01_exchange_microbench.md).  Groups are interleaved in
-//    a static order so one group's exchange latency hides behind the others' mat-vecs.
+//    contended flag lines (profiles/r01_exchange_microbench.md).
+//  * The 16 warps of a CTA are split into up to 3 TEAMS; team j advances groups j, j+T, ...
+//    on its own (named barriers, private staging buffers), so the exchange latency, sampling
+//    and pointwise phases of one group overlap the mat-vecs of the others.
 //  * The input layer I and every conditioning term are folded algebraically into the
 //    downstream layers at load time (host, fp64), so the recurrence only multiplies
 //    h1, h2, s=h1+h2, y1, y2; conditioning projections for step t+1 are computed during
 //    step t from TMA-staged rows of the UNFOLDED conditioning (fold gather fused).
+//  * Mat-vec work items use packed FFMA2 (fma.rn.f32x2, two folds per instruction, each lane
+//    IEEE-rounded exactly like fmaf) and a select-free butterfly reduce-scatter: weight rows
+//    and fold slots are pre-permuted per lane so every level is shuffle + add only.
 //  * Sampling (softmax inverse-CDF / mixture-of-logistics) is done redundantly by every
-//    CTA from the gathered logits, so no broadcast exchange is needed.
+//    CTA straight from the polled logits, so no broadcast exchange is needed.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,13 +33,17 @@ constexpr int BT = 8;             // folds per group (one 32-byte row of an exch
 constexpr int NTHREADS = 512;
 constexpr int NWARPS = NTHREADS / 32;
 constexpr int MAXG = 8;           // groups per launch -> 64 folds
+constexpr int MAXT = 3;           // teams per CTA
 constexpr int VEC = HID * BT;     // values of one exchanged vector (16 KiB in smem, 32 KiB of LL pairs in L2)
 constexpr int ITEM = 4 * 32 * 4;  // floats of one weight item image: 4 rows x 128 k
 constexpr int NEXCH = 5;
-constexpr int CONDK = 256;        // padded conditioning length (80 mel + 4*32 aux = 208)
+constexpr int CROW = 208;         // conditioning floats per fold-step: 80 mel + 4*32 aux
 constexpr int COND_ITEMS = 12;
+constexpr int PART_FLOATS = 32 * 32;   // per-team partial sums: up to 32 items x (4 rows x 8 folds)
 
 // ---- per-CTA weight image (floats) --------------------------------------------------------
+// An item image is [4 slots][32 lanes] float4: slot r of lane l holds W[row r ^ (l >> 3)][kbase + l + 32 i], i = 0..3
+// (the per-lane row permutation makes the butterfly reduce select-free, see reduce_scatter32).
 constexpr int W_M2 = 0;                       // 24 rows: Wih2x gates (12) | Whh1 gates (12), x H1
 constexpr int W_M3 = W_M2 + 24 * HID;         // 16 rows: Wfc1x (4) x H1 (S2) and x H2 (S3) | Whh2 gates (12) x H2
 constexpr int W_M4 = W_M3 + 16 * HID;         // 4 rows: Wfc2x x Y1
@@ -52,25 +60,32 @@ constexpr int PG_GH1 = 0, PG_GH2 = 96, PG_P1 = 192, PG_P2 = 288, PG_P3 = 384, PG
               PG_H1 = 448, PG_H2 = 480, PG_X = 512, PG_U = 520, PG_FX = 608, PG_F1 = 616, PG_SIZE = 656;
 
 // ---- shared memory map (floats) -----------------------------------------------------------
+// [weights | per-group state | fold ranges | profiling | team 0 | team 1 | team 2]
+// team block: [stage | part | cond staging (nbuf x 8 folds x 208) | 16 control words]
 struct SmemMap {
-    int w, stage, cx, cstage, part, priv, samp, tab, mbar, raw, total;
+    int w, priv, fs, prof, team0, team_stride, stage_floats, nbuf, total;
+    int t_stage, t_part, t_cst, t_ctl;      // offsets inside a team block
 };
-__host__ __device__ inline SmemMap smem_map(int rows5)
+__host__ __device__ inline int stage_floats_for(int mode, int C) { return (mode == 0 && BT * C > VEC) ? BT * C : VEC; }
+__host__ __device__ inline SmemMap smem_map(int rows5, int mode, int C, int T, int nbuf)
 {
     SmemMap m;
     m.w = 0;
-    m.stage = m.w + w_total(rows5);
-    m.cx = m.stage + (rows5 > 4 ? 9248 : 5152);     // >= VEC, and the fold-major logits image 8 x lg_row(C/32)
-    m.cstage = m.cx + CONDK * BT;
-    m.part = m.cstage + 2 * BT * 208;
-    m.priv = m.part + NWARPS * 32;
-    m.samp = m.priv + MAXG * PG_SIZE;
-    m.tab = m.samp + 1024;                          // work table: 4 item stages x 16 warps x int4
-    m.mbar = m.tab + 4 * NWARPS * 4;                // [0..3] cond mbarriers, [4,5] cond masks, [6] abort, [8,9] prefetch mbarrier
-    m.raw = m.mbar + 16;                            // TMA prefetch target: one exchanged vector as raw LL pairs (32 KiB)
-    m.total = m.raw + (rows5 > 4 ? 0 : 2 * VEC);    // (1024-class models run without the prefetch buffer)
+    m.priv = m.w + w_total(rows5);
+    m.fs = m.priv + MAXG * PG_SIZE;                 // [MAXG*8] fold starts | [MAXG*8] fold limits (long long)
+    m.prof = m.fs + 4 * MAXG * BT;
+    m.team0 = m.prof + 64;
+    m.stage_floats = stage_floats_for(mode, C);
+    m.nbuf = nbuf;
+    m.t_stage = 0;
+    m.t_part = m.t_stage + m.stage_floats;
+    m.t_cst = m.t_part + PART_FLOATS;
+    m.t_ctl = m.t_cst + nbuf * BT * CROW;           // [0..3] two mbarriers, [8] abort flag
+    m.team_stride = m.t_ctl + 16;
+    m.total = m.team0 + T * m.team_stride;
     return m;
 }
+__host__ __device__ constexpr int team_warps(int T) { return T == 1 ? 16 : T == 2 ? 8 : 5; }
 
 struct KParams {
     const float *wimg;                 // [NCTA][w_total]
@@ -84,12 +99,15 @@ struct KParams {
     unsigned long long seed;
     int B, S, G, C, mode, rows5, nprod5, n_u;   // n_u: uniforms per fold-step (1 RAW, 11 MOL)
     int feat, auxw;                    // 80, 128
+    int T, nbuf;                       // teams per CTA, conditioning staging buffers per team
+    int stagger;                       // start-up delay per team index (cycles): breaks the lockstep of the teams
     int group_fold0[MAXG], group_nf[MAXG];
     int probe_iters;
-    long long *prof;                   // optional [NCTA][PROF_SLOTS] per-stage cycle counters (clock64, thread 0)
+    long long *prof;                   // optional [NCTA][PROF_SLOTS] per-stage cycle counters (clock64, team 0 thread 0)
 };
 constexpr int PROF_SLOTS = 24;
-constexpr int XB_H1 = 0, XB_H2 = VEC, XB_Y1 = 2 * VEC, XB_Y2 = 3 * VEC, XB_LG = 4 * VEC;     // in pairs
+// exchange buffer of one group, in pairs: H1 | H2 | Y1 | Y2 as [k][8 folds], logits as [8 folds][cpad]
+constexpr int XB_H1 = 0, XB_H2 = VEC, XB_Y1 = 2 * VEC, XB_Y2 = 3 * VEC, XB_LG = 4 * VEC;
 __host__ __device__ constexpr int xb_group(int cpad) { return 4 * VEC + cpad * BT; }
 
 // ============================================================================================
@@ -101,16 +119,23 @@ __device__ __forceinline__ uint4 ld_pairs2(const unsigned long long *p)      // 
     asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ uint2 ld_pair(const unsigned long long *p)
+{
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_pair(unsigned long long *p, float v, unsigned epoch)   // one 8-byte store
 {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(epoch) : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_team(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-// physical index of (k, fold f) inside an exchanged vector: 32-byte rows, the two 16-byte
-// halves swapped on every other group of 4 rows so that 8 lanes reading 16 B at a 32 B
-// stride touch all 32 banks.
-__device__ __forceinline__ int xidx(int k, int f) { return k * BT + (f ^ (((k >> 2) & 1) << 2)); }
+// Shared-memory position of (k, fold f) of an exchanged vector: 32-byte rows [k][8]; fold f sits in slot
+// f ^ (k & 3).  A lane working on k = lane + 32 i loads the two 16-byte halves of its row in the order
+// (bit 2 of lane) first -- conflict-free -- and thereby finds fold (s ^ (lane & 7)) in register slot s.
+__device__ __forceinline__ int xidx(int k, int f) { return k * BT + (f ^ (k & 3)); }
 
 // mbarrier + 1-D bulk TMA (cp.async.bulk) -- conditioning rows are staged with these
 __device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
@@ -151,23 +176,21 @@ __device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * (1.0
 
 constexpr int POLL_CAP = 1 << 22;    // watchdog: ~1 s of polling
 
-// Fold-major shared-memory image of the RAW logits used by the sampler: fold f's classes are
-// contiguous, NPL = C/32 per lane with 4 floats of padding per lane (conflict-free LDS.128) and 4
-// more per fold row (conflict-free scatter from the LL gather).
-__host__ __device__ constexpr int lg_row(int npl) { return 32 * (npl + 4) + 4; }
-__device__ __forceinline__ int lg_idx(int npl, int k, int f)       // npl is a power of two
+// ---- packed fp32 math (Blackwell FFMA2): d.{x,y} = a.{x,y} * b.{x,y} + d.{x,y}, each half rounded like fmaf ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
 {
-    const int sh = 31 - __clz(npl);
-    return f * lg_row(npl) + (k >> sh) * (npl + 4) + (k & (npl - 1));
+    f32x2 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void fma2(f32x2 &d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
 
-// LL gather of `npairs` (multiple of 2) {value, epoch} pairs from L2 into the swizzled [k][8]
-// shared-memory layout; each thread polls its own 16-byte chunks until both epochs match.
-// Returns false if the watchdog fired (thread-local; the caller makes it CTA-uniform).
-// One work item: acc[4 rows][8 folds] += W[4][128 k] * X[128 k][8 folds].
-// wimg: item image [4][32 lanes] float4, element i of lane l = W[row][kbase + l + 32 i].
-// xs: exchanged vector in shared memory at row kbase (a multiple of 128); lane l consumes k = kbase + l + 32 i.
-__device__ __forceinline__ void item_fma(const float *wimg, const float *xs, int lane, float (&acc)[4][BT])
+// One work item: acc[slot r][fold slots] += W[4][128 k] * X[128 k][8 folds] for this lane's four k.
+// wimg: item image (see above).  xs: exchanged vector in shared memory at row kbase (a multiple of 128).
+// acc[r][j] holds fold slots (2j, 2j+1) of row slot r.
+__device__ __forceinline__ void item_fma(const float *wimg, const float *xs, int lane, f32x2 (&acc)[4][4])
 {
     float4 w[4];
 #pragma unroll
@@ -176,60 +199,98 @@ __device__ __forceinline__ void item_fma(const float *wimg, const float *xs, int
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float *xp = xs + (lane + 32 * i) * BT;
-        const float4 lo = *reinterpret_cast<const float4 *>(xp + sw);        // folds 0..3
-        const float4 hi = *reinterpret_cast<const float4 *>(xp + (4 - sw));  // folds 4..7
+        const float4 lo = *reinterpret_cast<const float4 *>(xp + sw);        // fold slots 0..3
+        const float4 hi = *reinterpret_cast<const float4 *>(xp + (4 - sw));  // fold slots 4..7
+        const f32x2 x0 = pack2(lo.x, lo.y), x1 = pack2(lo.z, lo.w), x2 = pack2(hi.x, hi.y), x3 = pack2(hi.z, hi.w);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const float wv = (i == 0) ? w[r].x : (i == 1) ? w[r].y : (i == 2) ? w[r].z : w[r].w;
-            acc[r][0] = fmaf(wv, lo.x, acc[r][0]);
-            acc[r][1] = fmaf(wv, lo.y, acc[r][1]);
-            acc[r][2] = fmaf(wv, lo.z, acc[r][2]);
-            acc[r][3] = fmaf(wv, lo.w, acc[r][3]);
-            acc[r][4] = fmaf(wv, hi.x, acc[r][4]);
-            acc[r][5] = fmaf(wv, hi.y, acc[r][5]);
-            acc[r][6] = fmaf(wv, hi.z, acc[r][6]);
-            acc[r][7] = fmaf(wv, hi.w, acc[r][7]);
+            const f32x2 ww = pack2(wv, wv);
+            fma2(acc[r][0], ww, x0);
+            fma2(acc[r][1], ww, x1);
+            fma2(acc[r][2], ww, x2);
+            fma2(acc[r][3], ww, x3);
+        }
+    }
+}
+// The same item against the fold-major conditioning staging buffer cst[fold][208] (k = kbase + lane + 32 i;
+// k >= 208 is the zero padding of the 256-wide conditioning K space).
+__device__ __forceinline__ void item_fma_cond(const float *wimg, const float *cst, int kbase, int lane, f32x2 (&acc)[4][4])
+{
+    float4 w[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const float4 *>(wimg + (r * 32 + lane) * 4);
+    const int fx = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k = kbase + lane + 32 * i;
+        float x[BT];
+#pragma unroll
+        for (int s = 0; s < BT; ++s) x[s] = (k < CROW) ? cst[(s ^ fx) * CROW + k] : 0.f;
+        const f32x2 x0 = pack2(x[0], x[1]), x1 = pack2(x[2], x[3]), x2 = pack2(x[4], x[5]), x3 = pack2(x[6], x[7]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float wv = (i == 0) ? w[r].x : (i == 1) ? w[r].y : (i == 2) ? w[r].z : w[r].w;
+            const f32x2 ww = pack2(wv, wv);
+            fma2(acc[r][0], ww, x0);
+            fma2(acc[r][1], ww, x1);
+            fma2(acc[r][2], ww, x2);
+            fma2(acc[r][3], ww, x3);
         }
     }
 }
 
-// Cross-lane reduce-scatter of the 32 accumulators: lane l returns the warp-wide sum of
-// acc[l >> 3][l & 7] (31 shuffles instead of 160).
-__device__ __forceinline__ float reduce_scatter32(float (&acc)[4][BT], int lane)
+// Cross-lane reduce-scatter of the 32 accumulator slots.  Slot (r, f) of lane l holds the partial sum of
+// (row r ^ (l >> 3), fold f ^ (l & 7)), so at every level both partners want to KEEP the lower half of their
+// slots and SEND the upper half: 31 shuffles + 31 adds, no selects.  Lane l returns the warp-wide sum of
+// (row l >> 3, fold l & 7).
+__device__ __forceinline__ float reduce_scatter32(f32x2 (&acc)[4][4])
 {
     float v[32];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int f = 0; f < BT; ++f) v[r * BT + f] = acc[r][f];
+        for (int j = 0; j < 4; ++j) unpack2(acc[r][j], v[r * 8 + 2 * j], v[r * 8 + 2 * j + 1]);
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
-        const bool upper = (lane & off) != 0;
 #pragma unroll
-        for (int j = 0; j < off; ++j) {
-            const float send = upper ? v[j] : v[j + off];
-            const float keep = upper ? v[j + off] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-        }
+        for (int j = 0; j < off; ++j) v[j] = v[j] + __shfl_xor_sync(0xffffffffu, v[j + off], off);
     }
     return v[0];
-}
-
-__device__ __forceinline__ void zero_acc(float (&acc)[4][BT])
-{
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int f = 0; f < BT; ++f) acc[r][f] = 0.f;
 }
 
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.0f / (1.0f + expf(-v)); }
 
 // Publish this CTA's 4 x 8 values of one exchanged vector: 32 lanes x 8-byte pairs = 256 contiguous
-// bytes.  Warp 0 only; lane = unit*8 + fold.  No fence, no flag: the epoch rides with the value.
+// bytes.  One warp; lane = unit*8 + fold.  No fence, no flag: the epoch rides with the value.
 __device__ __forceinline__ void publish_line(unsigned long long *vec, int cta, int lane, float val, unsigned epoch)
 {
     st_pair(vec + (UNITS * cta) * BT + lane, val, epoch);
+}
+
+// Shared-memory position of class k in a fold's logits row (RAW sampler): lane k / NPL owns NPL consecutive
+// classes; its float4 groups are XOR-swizzled so that the 16-byte reads of a quarter-warp hit distinct banks.
+template <int NPL>
+__device__ __forceinline__ int lg_swz(int owner)
+{
+    return NPL == 32 ? (owner & 7) : NPL == 16 ? ((owner >> 1) & 3) : NPL == 8 ? ((owner >> 2) & 1) : 0;
+}
+template <int NPL>
+__device__ __forceinline__ int lg_pos(int k)
+{
+    if (NPL < 4) return k;
+    const int owner = k / NPL, within = k % NPL;
+    return owner * NPL + ((((within >> 2) ^ lg_swz<NPL>(owner)) << 2) | (within & 3));
+}
+__device__ __forceinline__ int lg_pos_dyn(int npl, int k)
+{
+    switch (npl) {
+        case 32: return lg_pos<32>(k);
+        case 16: return lg_pos<16>(k);
+        case 8: return lg_pos<8>(k);
+        case 4: return lg_pos<4>(k);
+        default: return k;
+    }
 }
 
 // ============================================================================================
@@ -240,25 +301,22 @@ struct Ctx {
     float *sm;
     SmemMap m;
     int tid, lane, warp, cta;
-    int cond_visit;      // running count of conditioning visits (selects staging buffer / parity)
-    long long tprev;     // profiling: last timestamp (thread 0)
-    int pf_pending;      // a TMA prefetch of the next gather is in flight (CTA-uniform)
-    unsigned pf_parity;  // phase parity of the prefetch mbarrier
-    float du[3], dfx;    // draws fetched by draws_issue, waiting for draws_commit (warp 9)
-    // LL gather: this thread owns the 16-byte chunks i = tid + 512 j (unit/class k = i/4, folds 2(i%4), +1);
-    // their shared-memory destinations are affine in j, so the offsets are computed once.
-    int gv0;             // exchanged-vector layout: stage offset of chunk j = 0 (chunk j adds 1024 j)
-    int gl0, gl1, glj;   // fold-major logits image: offsets of the two folds of chunk 0, stride per chunk
+    int team, nw, nt, tw, ttid, ng;   // team index, warps / threads per team, warp / thread inside the team, groups of this team
+    float *stage, *part, *cst;        // this team's staging buffers
+    uint64_t *mbar;                   // this team's two conditioning mbarriers
+    int *abort_flag;
+    int cond_visit;      // running count of this team's conditioning visits (selects staging buffer / parity)
+    long long tprev;     // profiling: last timestamp (team 0, thread 0)
+    float du[3], dfx;    // draws fetched by draws_issue, waiting for draws_commit (last warp of the team)
 };
-// profiling tick: charge the cycles since the previous tick to `slot` (thread 0 of the CTA only).
-// Compiled out of the production kernel (PROF = false): the tick sites alone were ~5 KiB of code
-// and the step loop has to fit the instruction cache.
+// profiling tick: charge the cycles since the previous tick to `slot` (thread 0 of team 0 only).
+// Compiled out of the production kernel (PROF = false).
 template <bool PROF>
 __device__ __forceinline__ void tick(Ctx &c, int slot)
 {
     if (PROF && c.tid == 0) {
         const long long now = clock64();
-        reinterpret_cast<long long *>(c.sm + c.m.samp + 768)[slot] += now - c.tprev;
+        reinterpret_cast<long long *>(c.sm + c.m.prof)[slot] += now - c.tprev;
         c.tprev = now;
     }
 }
@@ -269,229 +327,112 @@ __device__ __forceinline__ unsigned long long *xb_base(const Ctx &c, int g)
 {
     return c.p->xb + (size_t)g * xb_group(c.p->rows5 * c.p->nprod5);
 }
+__device__ __forceinline__ void team_sync(const Ctx &c) { bar_team(1 + c.team, c.nt); }
 
-// LL gather of one exchanged vector (npairs {value, epoch} pairs) into the staging buffer.
-// Every thread loads its (up to 4 per batch) 16-byte chunks -- from the TMA-prefetched copy in
-// shared memory when there is one, else from L2 -- and re-polls L2 until both epochs of every
-// chunk match (all stale chunks are re-read together).  `logits` selects the fold-major image
-// consumed by the RAW sampler.  CTA-uniform result: false = the watchdog fired somewhere in
-// this CTA (the kernel then exits and the host reports WRNN_ERR_TIMEOUT).
-template <bool PROF>
-__device__ __forceinline__ bool cta_gather_direct(Ctx &c, const unsigned long long *src, int npairs, unsigned epoch, bool logits,
-                                                  const float *raw = nullptr)
+__device__ __forceinline__ void poll_timeout(Ctx &c)
 {
-    int *abort_flag = reinterpret_cast<int *>(c.sm + c.m.mbar + 6);
-    float *dst = c.sm + c.m.stage;
-    if (npairs == VEC) {
-        // the common case: exactly 4 chunks per thread, no bounds checks
+    *c.abort_flag = 1;
+    atomicExch(c.p->status, -4);
+}
+
+// LL gather of one exchanged vector (VEC {value, epoch} pairs, [k][8] in L2) into the team's staging
+// buffer.  Every thread polls 16-byte chunks (two pairs) in batches of four until both epochs match.
+// Team-uniform result: false = the watchdog fired somewhere in this team (the kernel then exits and the
+// host reports WRNN_ERR_TIMEOUT).
+template <bool PROF>
+__device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src, unsigned epoch)
+{
+    float *dst = c.stage;
+    constexpr int NCH = VEC / 2;
+#pragma unroll 1
+    for (int base = c.ttid; base < NCH; base += 4 * c.nt) {
         uint4 v[4];
-        const unsigned long long *gp = src + 2 * c.tid;
-        if (raw) {
+        bool need[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4 *>(raw + 4 * (c.tid + j * NTHREADS));
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = ld_pairs2(gp + 2 * j * NTHREADS);
+        for (int j = 0; j < 4; ++j) {
+            need[j] = base + j * c.nt < NCH;
+            if (need[j]) v[j] = ld_pairs2(src + 2 * (base + j * c.nt));
         }
         for (int spin = 0;; ++spin) {
-            const bool b0 = (v[0].y != epoch) | (v[0].w != epoch), b1 = (v[1].y != epoch) | (v[1].w != epoch),
-                       b2 = (v[2].y != epoch) | (v[2].w != epoch), b3 = (v[3].y != epoch) | (v[3].w != epoch);
-            if (!(b0 | b1 | b2 | b3)) break;
-            if (spin > POLL_CAP) {
-                *abort_flag = 1;
-                atomicExch(c.p->status, -4);
-                break;
-            }
-            if (PROF && c.tid == 0) reinterpret_cast<long long *>(c.sm + c.m.samp + 768)[raw ? 17 : 18] += 1;
-            if (b0) v[0] = ld_pairs2(gp);
-            if (b1) v[1] = ld_pairs2(gp + 2 * NTHREADS);
-            if (b2) v[2] = ld_pairs2(gp + 4 * NTHREADS);
-            if (b3) v[3] = ld_pairs2(gp + 6 * NTHREADS);
-        }
-        if (!logits) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float2 *>(dst + c.gv0 + j * 1024) = make_float2(__uint_as_float(v[j].x), __uint_as_float(v[j].z));
-        } else {
+            bool bad = false;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                dst[c.gl0 + j * c.glj] = __uint_as_float(v[j].x);
-                dst[c.gl1 + j * c.glj] = __uint_as_float(v[j].z);
+                const bool b = need[j] && ((v[j].y != epoch) | (v[j].w != epoch));
+                if (b) v[j] = ld_pairs2(src + 2 * (base + j * c.nt));
+                bad |= b;
+            }
+            if (!bad) break;
+            if (spin > POLL_CAP) {
+                poll_timeout(c);
+                break;
             }
         }
-    } else {
-        // any other size (MOL logits, RAW with C != 512): one chunk at a time
-        const int nchunks = npairs >> 1;
-#pragma unroll 1
-        for (int i = c.tid, j = 0; i < nchunks; i += NTHREADS, ++j) {
-            uint4 v = raw ? *reinterpret_cast<const uint4 *>(raw + 4 * i) : ld_pairs2(src + 2 * i);
-            for (int spin = 0; v.y != epoch || v.w != epoch; ++spin) {
-                if (spin > POLL_CAP) {
-                    *abort_flag = 1;
-                    atomicExch(c.p->status, -4);
-                    break;
-                }
-                v = ld_pairs2(src + 2 * i);
-            }
-            if (!logits) *reinterpret_cast<float2 *>(dst + c.gv0 + j * 1024) = make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
-            else {
-                dst[c.gl0 + j * c.glj] = __uint_as_float(v.x);
-                dst[c.gl1 + j * c.glj] = __uint_as_float(v.z);
-            }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!need[j]) continue;
+            const int i = base + j * c.nt, k = i >> 2, f0 = (i & 3) * 2;
+            // folds f0, f0+1 live in slots (f0 ^ (k&3)), (f0+1) ^ (k&3): an aligned pair, swapped when k is odd
+            const float a = __uint_as_float(v[j].x), b = __uint_as_float(v[j].z);
+            *reinterpret_cast<float2 *>(dst + k * BT + (f0 ^ (k & 2))) = (k & 1) ? make_float2(b, a) : make_float2(a, b);
         }
     }
     tick<PROF>(c, 19);                           // own chunks validated + scattered
-    __syncthreads();
+    team_sync(c);
     tick<PROF>(c, 20);                           // waiting for the other warps at the barrier
-    return *abort_flag == 0;
+    return *c.abort_flag == 0;
 }
 
-// The static visit order: for step t, stage 0 (SA) .. 4 (S5), groups 0..G-1 inside each stage.
-// Advance (t, stage, g) to the next visit that gathers a vector; false when there is none.
-__device__ __forceinline__ bool next_gather_visit(const KParams &p, int cta, int &t, int &stage, int &g)
-{
-    const int nst = cta < p.nprod5 ? 5 : 4;
-    for (;;) {
-        if (++g >= p.G) {
-            g = 0;
-            if (++stage >= nst) {
-                stage = 0;
-                ++t;
-            }
-        }
-        if (t > p.S) return false;
-        if (stage == 0) {
-            if (t > 0) return true;              // SA of step t samples the logits of step t-1
-        } else if (t < p.S)
-            return true;
-        else
-            return false;
-    }
-}
-__device__ __forceinline__ void visit_source(Ctx &c, int t, int stage, int g, const unsigned long long *&src, int &npairs, unsigned &epoch, bool &logits)
-{
-    const KParams &p = *c.p;
-    const unsigned long long *xb = xb_base(c, g);
-    if (stage == 0) {
-        src = xb + XB_LG;
-        npairs = p.rows5 * p.nprod5 * BT;
-        epoch = (unsigned)t;
-        logits = p.mode == 0;                   // RAW: fold-major image for the sampler; MOL: vector layout
-    } else {
-        src = xb + (stage - 1) * VEC;            // H1 | H2 | Y1 | Y2
-        npairs = VEC;
-        epoch = (unsigned)t + 1u;
-        logits = false;
-    }
-}
-
-// Gather the vector of visit (t, stage, g).  When a TMA prefetch of it was issued during the
-// previous visit, the pairs are taken from shared memory (stale ones -- a producer that had not
-// published yet -- are re-polled from L2); afterwards the NEXT visit's vector is prefetched with
-// one cp.async.bulk so its L2 latency overlaps this visit's mat-vecs.  With a single group the
-// next vector does not exist yet, so the prefetch is only used for G > 1.
-template <bool PROF>
-__device__ __forceinline__ bool cta_gather(Ctx &c, int t, int stage, int g)
-{
-    const KParams &p = *c.p;
-    const unsigned long long *src;
-    int npairs;
-    bool logits;
-    unsigned epoch;
-    visit_source(c, t, stage, g, src, npairs, epoch, logits);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(c.sm + c.m.mbar + 8);
-    const float *raw = nullptr;
-    if (c.pf_pending) {
-        while (!mbar_try_wait(bar, c.pf_parity)) {
-        }
-        c.pf_parity ^= 1u;
-        raw = c.sm + c.m.raw;
-        tick<PROF>(c, 16);                             // time spent waiting for the prefetch to land
-    }
-    const bool ok = cta_gather_direct<PROF>(c, src, npairs, epoch, logits, raw);   // ends with __syncthreads: raw is free again
-    // every visit but the very last one (SA of step S, last group) is followed by another gather
-    c.pf_pending = (p.G > 1 && p.rows5 <= 4 && !(t == p.S && g == p.G - 1)) ? 1 : 0;
-    if (c.pf_pending && c.tid == 0) {
-        int nt = t, ns = stage, ng = g;
-        next_gather_visit(p, c.cta, nt, ns, ng);
-        visit_source(c, nt, ns, ng, src, npairs, epoch, logits);
-        mbar_expect_tx(bar, (unsigned)npairs * 8u);
-        tma_bulk_g2s(c.sm + c.m.raw, src, (unsigned)npairs * 8u, bar);
-    }
-    return ok;
-}
-
-// Issue the TMA row copies of the conditioning for conditioning-visit v (group v % G, step v / G)
-// into staging buffer v & 1.  Called by ALL lanes of one warp: lane f < 8 copies fold f's two
-// rows (mel 320 B + aux 512 B).  Rows past fold_limit are the fold padding (zeros): they are
-// not copied, their bit stays clear in the validity mask and cond_visit writes zeros instead.
+// Conditioning visit v of this team is (group team + T * (v % ng), step v / ng).
+// Issue its TMA row copies into staging buffer v % nbuf.  Called by ALL lanes of one warp: lane f < 8
+// copies fold f's two rows (mel 320 B + aux 512 B).  Rows past fold_limit are the fold padding (zeros,
+// fatchord_version.py:306-309): they are not copied, the warp zero-fills them instead.
 __device__ __forceinline__ void cond_issue(Ctx &c, int v)
 {
     const KParams &p = *c.p;
-    const int g = v % p.G, step = v / p.G;
+    const int g = c.team + p.T * (v % c.ng), step = v / c.ng;
     if (step >= p.S) return;
-    float *buf = c.sm + c.m.cstage + (v & 1) * (BT * 208);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(c.sm + c.m.mbar) + (v & 1);
-    int *mask = reinterpret_cast<int *>(c.sm + c.m.mbar + 4) + (v & 1);
+    float *buf = c.cst + (v % p.nbuf) * (BT * CROW);
+    uint64_t *bar = c.mbar + (v % p.nbuf);
     const int f = c.lane;
     bool valid = false;
     long long row = 0;
     if (f < p.group_nf[g]) {
-        const long long *fs = reinterpret_cast<const long long *>(c.sm + c.m.samp);   // [MAXG*8] starts | [MAXG*8] limits
+        const long long *fs = reinterpret_cast<const long long *>(c.sm + c.m.fs);   // [MAXG*8] starts | [MAXG*8] limits
         row = fs[g * BT + f] + step;
         valid = row < fs[MAXG * BT + g * BT + f];
     }
-    const unsigned m = __ballot_sync(0xffffffffu, valid);
-    if (c.lane == 0) {
-        *mask = (int)m;
-        mbar_expect_tx(bar, (unsigned)(__popc(m) * (p.feat + p.auxw) * 4));
+    const unsigned m = __ballot_sync(0xffffffffu, valid) & 0xffu;
+    if (m != 0xffu) {
+        for (int ff = 0; ff < BT; ++ff)
+            if (!((m >> ff) & 1))
+                for (int i = c.lane; i < CROW; i += 32) buf[ff * CROW + i] = 0.f;
     }
+    // the staging buffer was last read through the generic proxy (work items, before the team barrier)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (c.lane == 0) mbar_expect_tx(bar, (unsigned)(__popc(m) * (p.feat + p.auxw) * 4));
     __syncwarp();
     if (valid) {
-        tma_bulk_g2s(buf + f * 208, p.mels + row * p.feat, (unsigned)(p.feat * 4), bar);
-        tma_bulk_g2s(buf + f * 208 + p.feat, p.aux + row * p.auxw, (unsigned)(p.auxw * 4), bar);
+        tma_bulk_g2s(buf + f * CROW, p.mels + row * p.feat, (unsigned)(p.feat * 4), bar);
+        tma_bulk_g2s(buf + f * CROW + p.feat, p.aux + row * p.auxw, (unsigned)(p.auxw * 4), bar);
     }
 }
 
-// Wait for conditioning visit v, transpose it into the [k][8] exchange layout (cx), and issue
-// the copies for visit v+1.  All threads; caller syncs before the items read cx.
-__device__ __forceinline__ void cond_visit(Ctx &c)
+// Wait until the conditioning rows of this team's next visit have landed.  All threads of the team.
+__device__ __forceinline__ void cond_wait(Ctx &c)
 {
     const KParams &p = *c.p;
-    const int v = c.cond_visit++;
-    const int step = v / p.G;
-    if (step >= p.S) return;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(c.sm + c.m.mbar) + (v & 1);
-    const unsigned parity = (unsigned)((v >> 1) & 1);
+    const int v = c.cond_visit;
+    if (v / c.ng >= p.S) return;
+    uint64_t *bar = c.mbar + (v % p.nbuf);
+    const unsigned parity = (unsigned)((v / p.nbuf) & 1);
     while (!mbar_try_wait(bar, parity)) {
     }
-    const int mask = reinterpret_cast<const int *>(c.sm + c.m.mbar + 4)[v & 1];
-    const float *buf = c.sm + c.m.cstage + (v & 1) * (BT * 208);
-    float *cx = c.sm + c.m.cx;
-    for (int i = c.tid; i < 208 * BT; i += NTHREADS) {
-        const int f = i / 208, k = i - f * 208;
-        cx[xidx(k, f)] = ((mask >> f) & 1) ? buf[i] : 0.f;
-    }
-    __syncthreads();                 // staging buffer (v+1)&1 was consumed one visit ago; cx complete
-    if (c.warp == NWARPS - 1) cond_issue(c, v + 1);
-}
-
-// Finalisation of the 12 conditioning items (work-table slots 4..15 of stage S4) into P1..P4 of group g.
-// item order: 0-2 P1 (chunk A) | 3-8 P2 (rg*2 + chunk) | 9,10 P3 (A,B) | 11 P4 (B)
-__device__ __forceinline__ void cond_finalize(Ctx &c, int g, int w)
-{
-    float *pg = priv(c, g);
-    const float *part = c.sm + c.m.part;
-    const int l = c.lane;
-    if (w >= 1 && w <= 3) pg[PG_P1 + (w - 1) * 32 + l] = part[(4 + (w - 1)) * 32 + l];
-    else if (w >= 4 && w <= 6) pg[PG_P2 + (w - 4) * 32 + l] = part[(4 + 3 + 2 * (w - 4)) * 32 + l] + part[(4 + 4 + 2 * (w - 4)) * 32 + l];
-    else if (w == 7) pg[PG_P3 + l] = part[(4 + 9) * 32 + l] + part[(4 + 10) * 32 + l];
-    else if (w == 8) pg[PG_P4 + l] = part[(4 + 11) * 32 + l];
 }
 
 // Fetch the uniforms / forced value that step `step` of group g will need at sampling time.
-// Two-phase so the global-load latency (injected uniforms) overlaps the gather + sampling of the
-// visit instead of making this warp late at the next block barrier: issue early, commit later.
+// Two-phase so the global-load latency (injected uniforms) overlaps the gather + items of the
+// visit: issue early, commit later.  Same warp for both.
 __device__ __forceinline__ void draws_issue(Ctx &c, int g, int step)
 {
     const KParams &p = *c.p;
@@ -533,218 +474,390 @@ __device__ __forceinline__ void draws_commit(Ctx &c, int g)
     if (c.lane < BT) pg[PG_FX + c.lane] = c.dfx;
 }
 
-// ---- sampling: logits of step s are in c.sm[stage]; writes the fed-back x into priv ----------
+// ---- sampling: logits of step s are polled straight from L2 ([fold][class] LL pairs); writes the fed-back x ----
 // RAW: softmax (fatchord_version.py:211) + inverse CDF with one uniform per fold (oracle/ref_shim.py:
-// k = #{c : cdf_c <= u}, clamped) + label -> float (:214).  One warp per fold, NPL = C/32 consecutive
-// classes per lane, warp shuffles only (no block barrier).
+// k = #{c : cdf_c <= u}, clamped) + label -> float (:214).  One warp per fold (a warp takes folds tw, tw + nw, ...),
+// NPL = C/32 consecutive classes per lane, warp shuffles only (no block barrier before the sample exists).
 template <int NPL>
-__device__ __forceinline__ void sample_raw(Ctx &c, int g, int s)
+__device__ __forceinline__ void sample_raw(Ctx &c, int g, int s, unsigned epoch)
 {
     const KParams &p = *c.p;
-    if (c.warp >= BT) return;
     float *pg = priv(c, g);
-    const int lane = c.lane, f = c.warp;
-    const float *row = c.sm + c.m.stage + f * lg_row(NPL) + lane * (NPL + 4);
-    float v[NPL];
-    if (NPL >= 4) {
+    const int lane = c.lane;
+    constexpr int C = NPL * 32;
+    constexpr int NCH = (NPL / 2) > 0 ? NPL / 2 : 1;        // 16-byte chunks (2 classes) per lane
+    constexpr int BATCH = NCH < 4 ? NCH : 4;
+    for (int f = c.tw; f < BT; f += c.nw) {
+        const unsigned long long *src = xb_base(c, g) + XB_LG + (size_t)f * C;
+        float *row = c.stage + f * C;
+#pragma unroll 1
+        for (int j0 = 0; j0 < NCH; j0 += BATCH) {
+            uint4 v[BATCH];
 #pragma unroll
-        for (int j = 0; j < NPL; j += 4) {
-            const float4 q = *reinterpret_cast<const float4 *>(row + j);
-            v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
-        }
-    } else {
+            for (int j = 0; j < BATCH; ++j) v[j] = ld_pairs2(src + 2 * ((j0 + j) * 32 + lane));
+            for (int spin = 0;; ++spin) {
+                bool bad = false;
 #pragma unroll
-        for (int j = 0; j < NPL; ++j) v[j] = row[j];
-    }
-    float m = v[0];
-#pragma unroll
-    for (int j = 1; j < NPL; ++j) m = fmaxf(m, v[j]);
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    float run = 0.f;                              // inclusive prefix inside the lane
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) {
-        run += expf(v[j] - m);
-        v[j] = run;
-    }
-    float incl = run;                             // inclusive scan of the lane totals across the warp
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const float t = __shfl_up_sync(0xffffffffu, incl, off);
-        if (lane >= off) incl += t;
-    }
-    const float excl = incl - run;
-    const float total = __shfl_sync(0xffffffffu, incl, 31);
-    const float thr = pg[PG_U + f * 11] * total;
-    int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < NPL; ++j) cnt += (excl + v[j] <= thr) ? 1 : 0;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
-    if (lane == 0) {
-        const int k = cnt > p.C - 1 ? p.C - 1 : cnt;
-        // 2 * k.float() / (C - 1.) - 1.  (fatchord_version.py:214), three separately rounded fp32 ops
-        const float sample = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, (float)k), (float)p.C - 1.0f), 1.0f);
-        if (f < p.group_nf[g] && c.cta == (s * p.G + g) % NCTA) {
-            const int b = p.group_fold0[g] + f;
-            p.samples_out[(size_t)b * p.S + s] = sample;
-            if (p.labels_out) p.labels_out[(size_t)b * p.S + s] = k;
-        }
-        pg[PG_X + f] = p.forced_x ? pg[PG_FX + f] : sample;
-    }
-}
-
-__device__ __forceinline__ void sample_mol(Ctx &c, int g, int s)
-{
-    // sample_from_discretized_mix_logistic, utility/distribution.py:87-123
-    const KParams &p = *c.p;
-    const float *lg = c.sm + c.m.stage;
-    float *pg = priv(c, g);
-    if (c.warp == 0) {
-        const int lane = c.lane, f = lane & 7, cs = lane >> 3;
-        const int nr = p.C / 3;
-        float best = -INFINITY;
-        int arg = 1 << 20;
-        for (int i = cs; i < nr; i += 4) {
-            const float u = (float)(1e-5 + ((1.0 - 1e-5) - 1e-5) * (double)pg[PG_U + f * 11 + i]);
-            const float t = lg[xidx(i, f)] - logf(-logf(u));
-            if (t > best) {
-                best = t;
-                arg = i;
+                for (int j = 0; j < BATCH; ++j) {
+                    const bool b = (v[j].y != epoch) | (v[j].w != epoch);
+                    if (b) v[j] = ld_pairs2(src + 2 * ((j0 + j) * 32 + lane));
+                    bad |= b;
+                }
+                if (!bad) break;
+                if (spin > POLL_CAP) {
+                    poll_timeout(c);
+                    break;
+                }
             }
-        }
 #pragma unroll
-        for (int off = 8; off <= 16; off <<= 1) {
-            const float b2 = __shfl_xor_sync(0xffffffffu, best, off);
-            const int a2 = __shfl_xor_sync(0xffffffffu, arg, off);
-            if (b2 > best || (b2 == best && a2 < arg)) {
-                best = b2;
-                arg = a2;
-            }
+            for (int j = 0; j < BATCH; ++j)
+                *reinterpret_cast<float2 *>(row + lg_pos<NPL>(2 * ((j0 + j) * 32 + lane))) =
+                    make_float2(__uint_as_float(v[j].x), __uint_as_float(v[j].z));
         }
-        if (cs == 0) {
-            const float mean = lg[xidx(nr + arg, f)];
-            const float ls = fmaxf(lg[xidx(2 * nr + arg, f)], -32.23619130191664f);
-            const float u2 = (float)(1e-5 + ((1.0 - 1e-5) - 1e-5) * (double)pg[PG_U + f * 11 + nr]);
-            float x = mean + expf(ls) * (logf(u2) - logf(1.0f - u2));
-            x = fminf(fmaxf(x, -1.0f), 1.0f);
+        __syncwarp();
+        float v[NPL];
+        if (NPL >= 4) {
+#pragma unroll
+            for (int j = 0; j < NPL; j += 4) {
+                const float4 q = *reinterpret_cast<const float4 *>(row + lane * NPL + (((j >> 2) ^ lg_swz<NPL>(lane)) << 2));
+                v[j] = q.x; v[j + 1] = q.y; v[j + 2] = q.z; v[j + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) v[j] = row[lane * NPL + j];
+        }
+        float m = v[0];
+#pragma unroll
+        for (int j = 1; j < NPL; ++j) m = fmaxf(m, v[j]);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+        float run = 0.f;                              // inclusive prefix inside the lane
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) {
+            run += expf(v[j] - m);
+            v[j] = run;
+        }
+        float incl = run;                             // inclusive scan of the lane totals across the warp
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const float t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const float excl = incl - run;
+        const float total = __shfl_sync(0xffffffffu, incl, 31);
+        const float thr = pg[PG_U + f * 11] * total;
+        int cnt = 0;
+#pragma unroll
+        for (int j = 0; j < NPL; ++j) cnt += (excl + v[j] <= thr) ? 1 : 0;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+        if (lane == 0) {
+            const int k = cnt > C - 1 ? C - 1 : cnt;
+            // 2 * k.float() / (C - 1.) - 1.  (fatchord_version.py:214), three separately rounded fp32 ops
+            const float sample = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, (float)k), (float)C - 1.0f), 1.0f);
             if (f < p.group_nf[g] && c.cta == (s * p.G + g) % NCTA) {
                 const int b = p.group_fold0[g] + f;
-                p.samples_out[(size_t)b * p.S + s] = x;
-                if (p.labels_out) p.labels_out[(size_t)b * p.S + s] = arg;
+                p.samples_out[(size_t)b * p.S + s] = sample;
+                if (p.labels_out) p.labels_out[(size_t)b * p.S + s] = k;
             }
-            pg[PG_X + f] = p.forced_x ? pg[PG_FX + f] : x;
+            pg[PG_X + f] = p.forced_x ? pg[PG_FX + f] : sample;
         }
     }
 }
 
-// logits_out[s][b][c] from the gathered logits (teacher-forced parity runs only)
+// sample_from_discretized_mix_logistic, utility/distribution.py:87-123.  Warp 0 of the team; the 30 logits of
+// the 8 folds are polled into stage[i * 8 + f].
+__device__ __forceinline__ void sample_mol(Ctx &c, int g, int s, unsigned epoch)
+{
+    const KParams &p = *c.p;
+    if (c.tw != 0) return;
+    float *lg = c.stage;
+    float *pg = priv(c, g);
+    const int lane = c.lane, f = lane & 7, cs = lane >> 3;
+    const int nr = p.C / 3, cpad = p.rows5 * p.nprod5;
+    const unsigned long long *src = xb_base(c, g) + XB_LG + (size_t)f * cpad;
+    for (int i = cs; i < p.C; i += 4) {
+        uint2 v = ld_pair(src + i);
+        for (int spin = 0; v.y != epoch; ++spin) {
+            if (spin > POLL_CAP) {
+                poll_timeout(c);
+                break;
+            }
+            v = ld_pair(src + i);
+        }
+        lg[i * BT + f] = __uint_as_float(v.x);
+    }
+    __syncwarp();
+    float best = -INFINITY;
+    int arg = 1 << 20;
+    for (int i = cs; i < nr; i += 4) {
+        const float u = (float)(1e-5 + ((1.0 - 1e-5) - 1e-5) * (double)pg[PG_U + f * 11 + i]);
+        const float t = lg[i * BT + f] - logf(-logf(u));
+        if (t > best) {
+            best = t;
+            arg = i;
+        }
+    }
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+        const float b2 = __shfl_xor_sync(0xffffffffu, best, off);
+        const int a2 = __shfl_xor_sync(0xffffffffu, arg, off);
+        if (b2 > best || (b2 == best && a2 < arg)) {
+            best = b2;
+            arg = a2;
+        }
+    }
+    if (cs == 0) {
+        const float mean = lg[(nr + arg) * BT + f];
+        const float ls = fmaxf(lg[(2 * nr + arg) * BT + f], -32.23619130191664f);
+        const float u2 = (float)(1e-5 + ((1.0 - 1e-5) - 1e-5) * (double)pg[PG_U + f * 11 + nr]);
+        float x = mean + expf(ls) * (logf(u2) - logf(1.0f - u2));
+        x = fminf(fmaxf(x, -1.0f), 1.0f);
+        if (f < p.group_nf[g] && c.cta == (s * p.G + g) % NCTA) {
+            const int b = p.group_fold0[g] + f;
+            p.samples_out[(size_t)b * p.S + s] = x;
+            if (p.labels_out) p.labels_out[(size_t)b * p.S + s] = arg;
+        }
+        pg[PG_X + f] = p.forced_x ? pg[PG_FX + f] : x;
+    }
+}
+
+// logits_out[s][b][c] from the staged logits (teacher-forced parity runs only; after the team barrier)
 __device__ __forceinline__ void dump_logits(Ctx &c, int g, int s)
 {
     const KParams &p = *c.p;
-    if (!p.logits_out || c.cta != (s * p.G + g) % NCTA) return;
-    const float *lg = c.sm + c.m.stage;
+    if (c.cta != (s * p.G + g) % NCTA) return;
+    const float *lg = c.stage;
     const int npl = p.mode == 0 ? p.C >> 5 : 0;
     for (int f = 0; f < p.group_nf[g]; ++f) {
         float *dst = p.logits_out + ((size_t)s * p.B + p.group_fold0[g] + f) * p.C;
-        for (int k = c.tid; k < p.C; k += NTHREADS) dst[k] = npl ? lg[lg_idx(npl, k, f)] : lg[xidx(k, f)];
+        for (int k = c.ttid; k < p.C; k += c.nt) dst[k] = npl ? lg[f * p.C + lg_pos_dyn(npl, k)] : lg[k * BT + f];
     }
 }
 
-// One copy of the mat-vec code serves every stage (the loop body must stay inside the 32 KiB
-// instruction cache: with the items inlined per stage the kernel was instruction-fetch bound,
-// profiles/r01_stage_cycles.md).  Work table entry of (stage, warp): x = weight image offset,
-// y = shared-memory offset of the first consumed row of the input vector, z = number of
-// consecutive 128-k items accumulated into one 4x8 tile (0 = warp idle in this stage).
-__device__ __forceinline__ void run_items(Ctx &c, int stage, bool enable)
+// The items of a stage are dealt round-robin to the warps of the team; item i leaves its 4 x 8 partial sums
+// in part[i * 32 + lane] (lane = row * 8 + fold), and the finalize roles add the K chunks in a fixed order,
+// so the arithmetic does not depend on the team size.  One copy of the mat-vec code serves every stage
+// (the loop body must stay inside the instruction cache).
+//   stage 1 (S2, x H1): 28 items = 7 row groups {Wih2x r,z,n | Whh1 r,z,n | Wfc1x} x 4 K chunks
+//   stage 2 (S3, x H2): 16 items = {Wfc1x | Whh2 r,z,n} x 4
+//   stage 3 (S4):       4 items Wfc2x x Y1, then the 12 conditioning items
+//   stage 4 (S5, x Y2): rows5 items = rows5/4 row groups x 4
+__device__ __forceinline__ void run_items(Ctx &c, int stage, bool run_main, bool run_cond)
 {
-    const int4 wk = reinterpret_cast<const int4 *>(c.sm + c.m.tab)[stage * NWARPS + c.warp];
-    if (wk.z == 0 || !enable) return;
-    float acc[4][BT];
-    zero_acc(acc);
-    for (int it = 0; it < wk.z; ++it) item_fma(c.sm + wk.x + it * ITEM, c.sm + wk.y + it * 128 * BT, c.lane, acc);
-    c.sm[c.m.part + c.warp * 32 + c.lane] = reduce_scatter32(acc, c.lane);
-}
-
-__device__ __forceinline__ void build_work_table(Ctx &c)
-{
-    if (c.tid >= 4 * NWARPS) return;
-    const int stage = c.tid / NWARPS, w = c.tid % NWARPS, rows5 = c.p->rows5;
-    int4 e = make_int4(0, 0, 0, 0);
-    const int W = c.m.w, X = c.m.stage;
-    if (stage == 0) {                                   // S2 (x H1): rg 0-2 Wih2x | 3-5 Whh1 | 6 Wfc1x; two K halves
-        if (w < 14) {
-            const int rg = w % 7, half = w / 7;
-            e = make_int4(W + (rg < 6 ? W_M2 + rg * 4 * ITEM : W_M3) + half * 2 * ITEM, X + half * 256 * BT, 2, 0);
-        }
-    } else if (stage == 1) {                            // S3 (x H2): warps 0-3 Wfc1x | 4-15 Whh2 (rg, kc)
-        const int rg = w < 4 ? 0 : 1 + (w - 4) % 3, kc = w < 4 ? w : (w - 4) / 3;
-        e = make_int4(W + W_M3 + (rg * 4 + kc) * ITEM, X + kc * 128 * BT, 1, 0);
-    } else if (stage == 2) {                            // S4: warps 0-3 Wfc2x x Y1 | 4-15 conditioning items x cx
-        if (w < 4) e = make_int4(W + W_M4 + w * ITEM, X + w * 128 * BT, 1, 0);
-        else {
-            const int it = w - 4;
+    const int rows5 = c.p->rows5;
+    const int n = stage == 1 ? 28 : stage == 4 ? rows5 : 16;
+    const float *W = c.sm + c.m.w;
+#pragma unroll 1
+    for (int i = c.tw; i < n; i += c.nw) {
+        f32x2 acc[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[r][j] = 0ull;
+        const int kc = i & 3;
+        if (stage == 3 && i >= 4) {
+            if (!run_cond) continue;
+            const int it = i - 4;
             const int chunk = (it < 3) ? 0 : (it < 9) ? ((it - 3) & 1) : (it == 9) ? 0 : 1;
-            e = make_int4(W + w_mc(rows5) + it * ITEM, c.m.cx + chunk * 128 * BT, 1, 0);
+            item_fma_cond(W + w_mc(rows5) + it * ITEM, c.cst + (c.cond_visit % c.p->nbuf) * (BT * CROW), chunk * 128, c.lane, acc);
+        } else {
+            if (!run_main) continue;
+            const int woff = stage == 1 ? (i < 24 ? W_M2 + i * ITEM : W_M3 + kc * ITEM)
+                           : stage == 2 ? W_M3 + i * ITEM
+                           : stage == 3 ? W_M4 + i * ITEM
+                                        : W_M5 + i * ITEM;
+            item_fma(W + woff, c.stage + kc * 128 * BT, c.lane, acc);
         }
-    } else {                                            // S5 (x Y2): rows5 / 4 row groups x 4 K chunks
-        if (w < rows5) e = make_int4(W + W_M5 + w * ITEM, X + (w & 3) * 128 * BT, 1, 0);
+        c.part[i * 32 + c.lane] = reduce_scatter32(acc);
     }
-    reinterpret_cast<int4 *>(c.sm + c.m.tab)[c.tid] = e;
+}
+__device__ __forceinline__ float sum4(const float *part, int rg, int lane)
+{
+    const float *q = part + rg * 128 + lane;
+    return (q[0] + q[32]) + (q[64] + q[96]);
+}
+
+// One visit: stage `stage` of step t for group g.  Returns false when the watchdog fired (team-uniform).
+template <bool PROF>
+__device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
+{
+    const KParams &p = *c.p;
+    const int S = p.S, lane = c.lane, tw = c.tw, nw = c.nw;
+    const unsigned epoch = (unsigned)t + 1u;
+    float *pg = priv(c, g);
+    unsigned long long *xb = xb_base(c, g);
+    const float *sv = small(c);
+    const float *part = c.part;
+    const bool warm = t < 0;
+
+    if (warm) team_sync(c);                              // no gather barrier in the warm-up pass: part is reused
+    if (stage == 3) {
+        cond_wait(c);                                    // conditioning rows of step t+1 of this group
+        tick<PROF>(c, 9);
+        if (tw == nw - 1 && !warm) draws_issue(c, g, t); // draws consumed by the sample of step t (at SA of t+1)
+    }
+    if (stage == 0) {
+        if (t > 0) {
+            // sample step t-1 from its logits (epoch t).  The barrier orders the draws committed at S4 (CTAs that
+            // do not produce logits come here straight from S4's finalize).
+            team_sync(c);
+            if (p.mode != 0) sample_mol(c, g, t - 1, (unsigned)t);
+            else switch (p.C) {
+                case 1024: sample_raw<32>(c, g, t - 1, (unsigned)t); break;
+                case 512: sample_raw<16>(c, g, t - 1, (unsigned)t); break;
+                case 256: sample_raw<8>(c, g, t - 1, (unsigned)t); break;
+                case 128: sample_raw<4>(c, g, t - 1, (unsigned)t); break;
+                default: sample_raw<2>(c, g, t - 1, (unsigned)t); break;
+            }
+            team_sync(c);
+            if (*c.abort_flag) return false;
+            tick<PROF>(c, 1);
+            if (p.logits_out) {
+                dump_logits(c, g, t - 1);
+                team_sync(c);                            // the staging buffer is reused by the next gather
+            }
+        }
+        if (t == S) return true;
+    } else {
+        if (!warm) {
+            if (!gather_vec<PROF>(c, xb + (stage - 1) * VEC, epoch)) return false;   // H1 | H2 | Y1 | Y2
+            tick<PROF>(c, 3 * stage + (stage >= 3 ? 1 : 0));
+        }
+        run_items(c, stage, !warm, t + 1 < S);
+        team_sync(c);
+        tick<PROF>(c, 3 * stage + 1 + (stage >= 3 ? 1 : 0));
+        if (stage == 3) {
+            // the staging buffer of this conditioning visit is free again: refill it for visit v + nbuf
+            if (tw == nw - 1) cond_issue(c, c.cond_visit + p.nbuf);
+            c.cond_visit += 1;
+        }
+    }
+
+    // ---- finalize: pointwise math of this CTA's 4 units x 8 folds, publish ----------------------
+    const int nroles = stage == 0 ? 1 : stage == 1 ? 5 : stage == 2 ? 4 : stage == 3 ? 8 : (p.rows5 >> 2);
+#pragma unroll 1
+    for (int role = tw; role < nroles; role += nw) {
+        if (stage <= 1) {
+            if (role == 0) {
+                // GRU cell (torch gate order r, z, n): stage 0 = rnn1 (input side folded into P1),
+                // stage 1 = rnn2 (input side = Wih2x . h1 from the items + P2)
+                const int u = lane >> 3, f = lane & 7;
+                const float x = pg[PG_X + f];
+                const int P = stage == 0 ? PG_P1 : PG_P2, GH = stage == 0 ? PG_GH1 : PG_GH2, H = stage == 0 ? PG_H1 : PG_H2;
+                const int SU = stage == 0 ? SV_U1 : SV_U2, SB = stage == 0 ? SV_B1 : SV_B2;
+                float gi[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    gi[q] = pg[P + q * 32 + lane] + x * sv[SU + q * 4 + u] + sv[SB + q * 4 + u];
+                    if (stage == 1) gi[q] += sum4(part, q, lane);
+                }
+                const float r = sigmoidf_(gi[0] + pg[GH + lane]);
+                const float z = sigmoidf_(gi[1] + pg[GH + 32 + lane]);
+                const float n = tanhf(gi[2] + r * pg[GH + 64 + lane]);
+                const float h = (1.0f - z) * n + z * pg[H + lane];
+                pg[H + lane] = h;
+                publish_line(xb + (stage == 0 ? XB_H1 : XB_H2), c.cta, lane, h, epoch);
+                tick<PROF>(c, stage == 0 ? 2 : 5);
+            } else if (role <= 3) {
+                const int q = role - 1;   // gh1 of the NEXT step: Whh1 . h1_t + b_hh1
+                pg[PG_GH1 + q * 32 + lane] = sum4(part, 3 + q, lane) + sv[SV_BHH1 + q * 4 + (lane >> 3)];
+            } else
+                pg[PG_F1 + lane] = sum4(part, 6, lane);                                    // Wfc1x . h1_t
+        } else if (stage == 2) {
+            // S3: fc1 (h2 part + saved h1 part); gh2 of the next step
+            if (role == 0) {
+                const int u = lane >> 3, f = lane & 7;
+                float y = (sum4(part, 0, lane) + pg[PG_F1 + lane]) + pg[PG_P3 + lane] + pg[PG_X + f] * sv[SV_U3 + u] + sv[SV_B3 + u];
+                y = fmaxf(y, 0.f);
+                publish_line(xb + XB_Y1, c.cta, lane, y, epoch);
+                tick<PROF>(c, 8);
+            } else {
+                const int q = role - 1;
+                pg[PG_GH2 + q * 32 + lane] = sum4(part, 1 + q, lane) + sv[SV_BHH2 + q * 4 + (lane >> 3)];
+            }
+        } else if (stage == 3) {
+            // S4: fc2; conditioning projections of step t+1
+            // cond item order: 0-2 P1 (chunk A) | 3-8 P2 (rg*2 + chunk) | 9,10 P3 (A,B) | 11 P4 (B); part slot = 4 + item
+            if (role == 0) {
+                if (!warm) {
+                    float y = sum4(part, 0, lane) + pg[PG_P4 + lane] + sv[SV_B4 + (lane >> 3)];
+                    y = fmaxf(y, 0.f);
+                    publish_line(xb + XB_Y2, c.cta, lane, y, epoch);
+                    tick<PROF>(c, 12);
+                }
+                if (t + 1 < S) pg[PG_P4 + lane] = part[(4 + 11) * 32 + lane];
+            } else if (t + 1 < S) {
+                if (role <= 3) pg[PG_P1 + (role - 1) * 32 + lane] = part[(4 + (role - 1)) * 32 + lane];
+                else if (role <= 6) pg[PG_P2 + (role - 4) * 32 + lane] = part[(4 + 3 + 2 * (role - 4)) * 32 + lane] + part[(4 + 4 + 2 * (role - 4)) * 32 + lane];
+                else pg[PG_P3 + lane] = part[(4 + 9) * 32 + lane] + part[(4 + 10) * 32 + lane];
+            }
+        } else {
+            // S5: logits of this CTA's rows5 classes, published fold-major
+            const float v = sum4(part, role, lane) + sv[SV_B5 + role * 4 + (lane >> 3)];
+            const int k = p.rows5 * c.cta + role * 4 + (lane >> 3);
+            st_pair(xb + XB_LG + (size_t)(lane & 7) * (p.rows5 * p.nprod5) + k, v, epoch);
+            tick<PROF>(c, 15);
+        }
+    }
+    if (stage == 3 && tw == nw - 1 && !warm) draws_commit(c, g);
+    return true;
 }
 
 template <bool PROF>
 __device__ __forceinline__ void persistent_body(const KParams &prm)
 {
     extern __shared__ __align__(128) float sm[];
+    const KParams &p = prm;
     Ctx c;
     c.p = &prm;
     c.sm = sm;
-    c.m = smem_map(prm.rows5);
+    c.m = smem_map(p.rows5, p.mode, p.C, p.T, p.nbuf);
     c.tid = threadIdx.x;
     c.lane = c.tid & 31;
     c.warp = c.tid >> 5;
     c.cta = blockIdx.x;
+    c.nw = team_warps(p.T);
+    c.nt = c.nw * 32;
+    c.team = c.warp / c.nw;
+    c.tw = c.warp - c.team * c.nw;
+    c.ttid = c.tid - c.team * c.nt;
     c.cond_visit = 0;
     c.tprev = 0;
-    c.pf_pending = 0;
-    c.pf_parity = 0;
-    {   // scatter offsets of this thread's gather chunks (see Ctx)
-        const int k0 = c.tid >> 2, f0 = (c.tid & 3) * 2;
-        c.gv0 = xidx(k0, f0);
-        const int npl = prm.mode == 0 ? prm.C >> 5 : 32;
-        c.gl0 = lg_idx(npl, k0, f0);
-        c.gl1 = lg_idx(npl, k0, f0 + 1);
-        c.glj = (128 / npl) * (npl + 4);
+    const bool member = c.team < p.T;
+    c.ng = member ? (p.G - c.team + p.T - 1) / p.T : 0;
+    {
+        float *tb = sm + c.m.team0 + (member ? c.team : 0) * c.m.team_stride;
+        c.stage = tb + c.m.t_stage;
+        c.part = tb + c.m.t_part;
+        c.cst = tb + c.m.t_cst;
+        c.mbar = reinterpret_cast<uint64_t *>(tb + c.m.t_ctl);
+        c.abort_flag = reinterpret_cast<int *>(tb + c.m.t_ctl + 8);
     }
-    const KParams &p = prm;
     const int G = p.G, S = p.S;
-    const int lane = c.lane, w = c.warp;
 
-    // ---- prologue: resident weights, zero state ------------------------------------------------
+    // ---- prologue (whole CTA): resident weights, zero state ------------------------------------
     {
         const float4 *src = reinterpret_cast<const float4 *>(p.wimg + (size_t)c.cta * w_total(p.rows5));
         float4 *dst = reinterpret_cast<float4 *>(sm + c.m.w);
         for (int i = c.tid; i < w_total(p.rows5) / 4; i += NTHREADS) dst[i] = src[i];
-        for (int i = c.tid; i < CONDK * BT; i += NTHREADS) sm[c.m.cx + i] = 0.f;
         for (int i = c.tid; i < MAXG * PG_SIZE; i += NTHREADS) sm[c.m.priv + i] = 0.f;
-        build_work_table(c);
         if (c.tid < MAXG * BT) {                 // fold row ranges cached in shared memory (cond_issue reads them every visit)
             const int g = c.tid / BT, f = c.tid % BT;
-            long long *fs = reinterpret_cast<long long *>(sm + c.m.samp);
+            long long *fs = reinterpret_cast<long long *>(sm + c.m.fs);
             const bool live = g < p.G && f < p.group_nf[g];
             fs[c.tid] = live ? p.fold_start[p.group_fold0[g] + f] : 0;
             fs[MAXG * BT + c.tid] = live ? p.fold_limit[p.group_fold0[g] + f] : 0;
         }
-        if (c.tid == 0) {
-            uint64_t *bar = reinterpret_cast<uint64_t *>(sm + c.m.mbar);
+        if (c.tid < p.T) {
+            float *tb = sm + c.m.team0 + c.tid * c.m.team_stride;
+            uint64_t *bar = reinterpret_cast<uint64_t *>(tb + c.m.t_ctl);
             mbar_init(bar, 1);
             mbar_init(bar + 1, 1);
-            mbar_init(bar + 4, 1);               // prefetch barrier (floats [8,9] of the mbar block)
-            *reinterpret_cast<int *>(sm + c.m.mbar + 6) = 0;
+            *reinterpret_cast<int *>(tb + c.m.t_ctl + 8) = 0;
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        if (c.tid < 2 * PROF_SLOTS) sm[c.m.samp + 768 + c.tid] = 0.f;
+        if (c.tid < 64) sm[c.m.prof + c.tid] = 0.f;
         __syncthreads();
         const float *sv = small(c);
         for (int g = 0; g < G; ++g) {           // h = 0  =>  gh = b_hh  (fatchord_version.py:173-174)
@@ -754,146 +867,61 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
                 pg[PG_GH2 + c.tid] = sv[SV_BHH2 + (c.tid >> 3)];
             }
         }
+        __syncthreads();
     }
+    if (!member) return;                         // spare warp (3 teams x 5 warps)
+    if (c.tw == c.nw - 1)
+        for (int v = 0; v < p.nbuf; ++v) cond_issue(c, v);
 
+    if (c.team > 0 && p.stagger > 0) {
+        // Teams that start together stay in lockstep (all in their mat-vecs, then all waiting on an exchange);
+        // a one-time offset lets one team's exchange latency hide behind the others' math.
+        const long long t0 = clock64(), wait = (long long)c.team * p.stagger;
+        while (clock64() - t0 < wait) {
+        }
+    }
     if (PROF && c.tid == 0) c.tprev = clock64();
-    // t = -1 is the warm-up pass: only the conditioning half of stage 3 runs (projections of step 0),
-    // so every helper below has exactly ONE call site -- the step loop must fit the instruction cache.
+    // t = -1 is the warm-up pass: only the conditioning half of stage 3 runs (projections of step 0).
+    // Visit order inside a team: stage-major, its groups inside each stage, so that with several groups
+    // per team one group's exchange still overlaps the others' mat-vecs.
     for (int t = -1; t <= S; ++t) {
-        const unsigned epoch = (unsigned)t + 1u;
-        // stage 0 = SA (sample step t-1, GRU1 of step t); 1..4 = S2..S5.  Groups are visited in a
-        // static order inside each stage so one group's exchange overlaps the others' mat-vecs.
         for (int stage = (t < 0 ? 3 : 0); stage < (t < 0 ? 4 : 5); ++stage) {
             if (stage == 4 && c.cta >= p.nprod5) break;            // only the logits producers run S5
             if (stage > 0 && t == S) break;
-            for (int g = 0; g < G; ++g) {
-                float *pg = priv(c, g);
-                unsigned long long *xb = xb_base(c, g);
-                const float *sv = small(c);
-                const float *part = sm + c.m.part;
-                const bool warm = t < 0;
-                if (stage == 3) {
-                    if (t == -1 && g == 0 && w == NWARPS - 1) cond_issue(c, 0);
-                    if (t == -1 && g == 0) __syncthreads();
-                    cond_visit(c);               // stages cond(t+1) of this group, prefetches the next visit
-                    tick<PROF>(c, 9);
-                    if (w == 9 && !warm) draws_issue(c, g, t);     // draws consumed by the sample of step t (at SA of t+1)
-                }
-                if (!warm && (stage > 0 || t > 0)) {
-                    if (!cta_gather<PROF>(c, t, stage, g)) return;  // LG (t-1) | H1 | H2 | Y1 | Y2
-                    tick<PROF>(c, 3 * stage + (stage >= 3 ? 1 : 0));
-                }
-                if (stage == 0) {
-                    if (t > 0) {
-                        dump_logits(c, g, t - 1);
-                        if (p.mode != 0) sample_mol(c, g, t - 1);
-                        else switch (p.C) {
-                            case 1024: sample_raw<32>(c, g, t - 1); break;
-                            case 512: sample_raw<16>(c, g, t - 1); break;
-                            case 256: sample_raw<8>(c, g, t - 1); break;
-                            case 128: sample_raw<4>(c, g, t - 1); break;
-                            default: sample_raw<2>(c, g, t - 1); break;
-                        }
-                        __syncthreads();
-                        tick<PROF>(c, 1);
-                    }
-                    if (t == S) continue;
-                } else {
-                    run_items(c, stage - 1, !warm ? (stage != 3 || w < 4 || t + 1 < S) : (w >= 4));
-                    __syncthreads();
-                    tick<PROF>(c, 3 * stage + 1 + (stage >= 3 ? 1 : 0));
-                }
-                // ---- finalize: pointwise math of this CTA's 4 units x 8 folds, publish --------------
-                if (stage <= 1) {
-                    if (w == 0) {
-                        // GRU cell (torch gate order r, z, n): stage 0 = rnn1 (input side folded into P1),
-                        // stage 1 = rnn2 (input side = Wih2x . h1 from the items + P2)
-                        const int u = lane >> 3, f = lane & 7;
-                        const float x = pg[PG_X + f];
-                        const int P = stage == 0 ? PG_P1 : PG_P2, GH = stage == 0 ? PG_GH1 : PG_GH2, H = stage == 0 ? PG_H1 : PG_H2;
-                        const int SU = stage == 0 ? SV_U1 : SV_U2, SB = stage == 0 ? SV_B1 : SV_B2;
-                        float gi[3];
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            gi[q] = pg[P + q * 32 + lane] + x * sv[SU + q * 4 + u] + sv[SB + q * 4 + u];
-                            if (stage == 1) gi[q] += part[q * 32 + lane] + part[(7 + q) * 32 + lane];
-                        }
-                        const float r = sigmoidf_(gi[0] + pg[GH + lane]);
-                        const float z = sigmoidf_(gi[1] + pg[GH + 32 + lane]);
-                        const float n = tanhf(gi[2] + r * pg[GH + 64 + lane]);
-                        const float h = (1.0f - z) * n + z * pg[H + lane];
-                        pg[H + lane] = h;
-                        publish_line(xb + (stage == 0 ? XB_H1 : XB_H2), c.cta, lane, h, epoch);
-                        tick<PROF>(c, stage == 0 ? 2 : 5);
-                    } else if (stage == 1) {
-                        if (w <= 3) {
-                            const int q = w - 1; // gh1 of the NEXT step: Whh1 . h1_t + b_hh1
-                            pg[PG_GH1 + q * 32 + lane] = (part[(3 + q) * 32 + lane] + part[(10 + q) * 32 + lane]) + sv[SV_BHH1 + q * 4 + (lane >> 3)];
-                        } else if (w == 4)
-                            pg[PG_F1 + lane] = part[6 * 32 + lane] + part[13 * 32 + lane];      // Wfc1x . h1_t
-                    }
-                } else if (stage == 2) {
-                    // S3: fc1 (h2 part + saved h1 part); gh2 of the next step
-                    if (w == 0) {
-                        const int u = lane >> 3, f = lane & 7;
-                        float y = (((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + pg[PG_F1 + lane]) + pg[PG_P3 + lane] + pg[PG_X + f] * sv[SV_U3 + u] + sv[SV_B3 + u];
-                        y = fmaxf(y, 0.f);
-                        publish_line(xb + XB_Y1, c.cta, lane, y, epoch);
-                        tick<PROF>(c, 8);
-                    } else if (w <= 3) {
-                        const int q = w - 1, s0 = 4 + q;
-                        pg[PG_GH2 + q * 32 + lane] = ((part[s0 * 32 + lane] + part[(s0 + 3) * 32 + lane]) + (part[(s0 + 6) * 32 + lane] + part[(s0 + 9) * 32 + lane])) + sv[SV_BHH2 + q * 4 + (lane >> 3)];
-                    }
-                } else if (stage == 3) {
-                    // S4: fc2; conditioning projections of step t+1; draws of step t
-                    if (w == 0 && !warm) {
-                        float y = ((part[lane] + part[32 + lane]) + (part[64 + lane] + part[96 + lane])) + pg[PG_P4 + lane] + sv[SV_B4 + (lane >> 3)];
-                        y = fmaxf(y, 0.f);
-                        publish_line(xb + XB_Y2, c.cta, lane, y, epoch);
-                        tick<PROF>(c, 12);
-                    }
-                    __syncwarp();
-                    if (t + 1 < S) {
-                        if (w == 0) pg[PG_P4 + lane] = part[(4 + 11) * 32 + lane];
-                        else if (w != 8) cond_finalize(c, g, w);
-                    }
-                    if (w == 9 && !warm) draws_commit(c, g);
-                } else {
-                    // S5: logits of this CTA's rows5 classes
-                    if (w * 4 < p.rows5) {
-                        const float *pw = part + w * 128;
-                        const float v = ((pw[lane] + pw[32 + lane]) + (pw[64 + lane] + pw[96 + lane])) + sv[SV_B5 + w * 4 + (lane >> 3)];
-                        const int k = p.rows5 * c.cta + w * 4 + (lane >> 3);
-                        st_pair(xb + XB_LG + k * BT + (lane & 7), v, epoch);
-                    }
-                    tick<PROF>(c, 15);
-                }
-            }
+            for (int g = c.team; g < G; g += p.T)
+                if (!visit<PROF>(c, t, stage, g)) return;
         }
     }
     if (PROF && p.prof && c.tid == 0)
-        for (int i = 0; i < PROF_SLOTS; ++i) p.prof[(size_t)c.cta * PROF_SLOTS + i] = reinterpret_cast<long long *>(sm + c.m.samp + 768)[i];
+        for (int i = 0; i < PROF_SLOTS; ++i) p.prof[(size_t)c.cta * PROF_SLOTS + i] = reinterpret_cast<long long *>(sm + c.m.prof)[i];
 }
 
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel(const KParams prm) { persistent_body<false>(prm); }
 // same kernel with the per-stage clock64 accounting compiled in (wrnn_set_profiling)
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel_prof(const KParams prm) { persistent_body<true>(prm); }
 
-// Exchange microbenchmark: the same publish / LL-gather sequence on an otherwise empty kernel.
+// Exchange microbenchmark: the same publish / LL-gather sequence on an otherwise empty kernel (one team).
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe_kernel(const KParams prm)
 {
     extern __shared__ __align__(128) float sm[];
     Ctx c;
     c.p = &prm;
     c.sm = sm;
-    c.m = smem_map(prm.rows5);
+    c.m = smem_map(prm.rows5, prm.mode, prm.C, 1, 1);
     c.tid = threadIdx.x;
     c.lane = c.tid & 31;
     c.warp = c.tid >> 5;
     c.cta = blockIdx.x;
-    c.gv0 = xidx(c.tid >> 2, (c.tid & 3) * 2);
-    c.gl0 = c.gl1 = c.glj = 0;
-    if (c.tid == 0) *reinterpret_cast<int *>(sm + c.m.mbar + 6) = 0;
+    c.team = 0;
+    c.nw = NWARPS;
+    c.nt = NTHREADS;
+    c.tw = c.warp;
+    c.ttid = c.tid;
+    c.tprev = 0;
+    float *tb = sm + c.m.team0;
+    c.stage = tb + c.m.t_stage;
+    c.abort_flag = reinterpret_cast<int *>(tb + c.m.t_ctl + 8);
+    if (c.tid == 0) *c.abort_flag = 0;
     __syncthreads();
     unsigned long long *xb = xb_base(c, 0);
     float acc = 0.f;
@@ -901,8 +929,8 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe
         unsigned long long *vec = xb + (it & 3) * VEC;
         const unsigned epoch = (unsigned)it + 1u;
         if (c.warp == 0) publish_line(vec, c.cta, c.lane, acc + (float)it, epoch);
-        if (!cta_gather_direct<false>(c, vec, VEC, epoch, false)) return;
-        acc += sm[c.m.stage + c.tid] * 1e-30f;
+        if (!gather_vec<false>(c, vec, epoch)) return;
+        acc += c.stage[c.tid] * 1e-30f;
         __syncthreads();
     }
     if (acc == 123.456f) prm.status[1] = 1;      // keep the loads alive

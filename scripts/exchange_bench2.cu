@@ -1,0 +1,378 @@
+// Microbenchmarks that decide the round-1 kernel structure on B200 (development aid, not product):
+//   A. grid-level all-gather protocols: {value, epoch} LL pairs vs in-band poison (no flags), replicas,
+//      payload slope, and 3 concurrent 160-thread teams vs one 512-thread team.
+//   B. per-SM math rates: the FFMA work item (weights + inputs from shared memory), the same with the
+//      weights held in registers, mma.sync m16n8k8 TF32 (3xTF32 = 3 of these per tile) and m16n8k16 BF16.
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o exchange_bench2 exchange_bench2.cu
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+constexpr int NT = 512;
+constexpr unsigned POISON = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint4 ld_volatile4(const void *p) { uint4 v; asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void st_volatile(void *p, unsigned v) { asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_pair(void *p, float v, unsigned e) { asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(e) : "memory"); }
+__device__ __forceinline__ void team_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// ---- A. exchange -----------------------------------------------------------------------------
+// mode 0: LL pairs, 32 KiB per vector, 512 threads
+// mode 1: poison, `lines` 128-byte lines per vector (CTA c publishes line c when c < lines), R replicas, 512 threads
+// mode 2: poison, 3 teams x 160 threads, each team exchanges its own vector every iteration
+// mode 3: poison, one team of 160 threads (the other warps idle)
+// buffers: [team 3][slot 3][replica 4][4096 floats]; slot (it+2)%3 is poisoned after gathering iteration it
+__global__ void __launch_bounds__(NT, 1) exch(int mode, int iters, int lines, int R, unsigned *buf, unsigned long long *ll, int *errors, float *sink)
+{
+    extern __shared__ float sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x;
+    float acc = 0.f;
+    int err = 0, cap = 1 << 18;
+    if (mode == 0) {
+        for (int it = 0; it < iters; ++it) {
+            const unsigned epoch = it + 1;
+            unsigned long long *lb = ll + (size_t)(it % 5) * 4096;
+            if (warp == 0) st_pair(lb + cta * 32 + lane, (float)(it + cta), epoch);
+            uint4 v[4];
+            for (int j = 0; j < 4; ++j) v[j] = ld_volatile4(lb + 2 * (tid + j * NT));
+            for (int spin = 0;; ++spin) {
+                if (spin > cap) { err += 1000000; cap = 0; break; }
+                bool bad = false;
+                for (int j = 0; j < 4; ++j) {
+                    const bool b = v[j].y != epoch || v[j].w != epoch;
+                    if (b) v[j] = ld_volatile4(lb + 2 * (tid + j * NT));
+                    bad |= b;
+                }
+                if (!bad) break;
+            }
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<float2 *>(sm + 2 * (tid + j * NT)) = make_float2(__uint_as_float(v[j].x), __uint_as_float(v[j].z));
+            __syncthreads();
+            acc += sm[tid] * 1e-30f;
+            __syncthreads();
+        }
+    } else {
+        int team = 0, tn = NT, ttid = tid, nteam = 1;
+        if (mode == 2 || mode == 3) {
+            team = warp / 5; tn = 160; ttid = tid - team * 160; nteam = 3;
+            if (team >= 3 || (mode == 3 && team > 0)) return;
+        }
+        float *st = sm + team * 4096;
+        const int nchunk = lines * 8;                                 // 16-byte chunks of the vector
+        for (int it = 0; it < iters; ++it) {
+            const int slot = it % 3;
+            unsigned *base = buf + ((size_t)(team * 3 + slot) * 4) * 4096;
+            unsigned *other = buf + ((size_t)(team * 3 + (it + 2) % 3) * 4) * 4096;
+            if (ttid < 32 && cta < lines)
+                for (int r = 0; r < R; ++r) st_volatile(base + r * 4096 + cta * 32 + lane, __float_as_uint((float)(it + cta)));
+            const unsigned *src = base + (cta % R) * 4096;
+            for (int i0 = ttid; i0 < nchunk; i0 += 4 * tn) {
+                uint4 v[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (i0 + j * tn < nchunk) v[j] = ld_volatile4(src + 4 * (i0 + j * tn));
+                for (int spin = 0;; ++spin) {
+                    if (spin > cap) { err += 1000000; cap = 0; break; }
+                    bool bad = false;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (i0 + j * tn < nchunk) {
+                        const bool b = v[j].x == POISON || v[j].y == POISON || v[j].z == POISON || v[j].w == POISON;
+                        if (b) v[j] = ld_volatile4(src + 4 * (i0 + j * tn));
+                        bad |= b;
+                    }
+                    if (!bad) break;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (i0 + j * tn < nchunk) *reinterpret_cast<uint4 *>(st + 4 * (i0 + j * tn)) = v[j];
+            }
+            if (nteam == 1) __syncthreads(); else team_bar(1 + team, tn);
+            // poison my line of the other slot (it held step it-1, which every CTA has finished reading)
+            if (ttid < 32 && cta < lines)
+                for (int r = 0; r < R; ++r) st_volatile(other + r * 4096 + cta * 32 + lane, POISON);
+            // verify: line c must hold it + c
+            for (int i = ttid; i < lines * 32; i += tn) if (st[i] != (float)(it + i / 32)) ++err;
+            acc += st[ttid] * 1e-30f;
+            if (nteam == 1) __syncthreads(); else team_bar(1 + team, tn);
+        }
+    }
+    if (err) atomicAdd(errors, err);
+    if (acc == 1234.5f) sink[0] = acc;
+}
+
+// ---- B. math rates ----------------------------------------------------------------------------
+// Every warp runs `iters` work items; smem holds 16 item images (weights) and one 512 x 8 input vector.
+__device__ __forceinline__ void item_fma(const float *wimg, const float *xs, int lane, float (&acc)[4][8])
+{
+    float4 w[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const float4 *>(wimg + (r * 32 + lane) * 4);
+    const int sw = ((lane >> 2) & 1) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float *xp = xs + (lane + 32 * i) * 8;
+        const float4 lo = *reinterpret_cast<const float4 *>(xp + sw);
+        const float4 hi = *reinterpret_cast<const float4 *>(xp + (4 - sw));
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float wv = (i == 0) ? w[r].x : (i == 1) ? w[r].y : (i == 2) ? w[r].z : w[r].w;
+            acc[r][0] = fmaf(wv, lo.x, acc[r][0]); acc[r][1] = fmaf(wv, lo.y, acc[r][1]);
+            acc[r][2] = fmaf(wv, lo.z, acc[r][2]); acc[r][3] = fmaf(wv, lo.w, acc[r][3]);
+            acc[r][4] = fmaf(wv, hi.x, acc[r][4]); acc[r][5] = fmaf(wv, hi.y, acc[r][5]);
+            acc[r][6] = fmaf(wv, hi.z, acc[r][6]); acc[r][7] = fmaf(wv, hi.w, acc[r][7]);
+        }
+    }
+}
+__device__ __forceinline__ float reduce_scatter32(float (&acc)[4][8], int lane)
+{
+    float v[32];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int f = 0; f < 8; ++f) v[r * 8 + f] = acc[r][f];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+            const float send = upper ? v[j] : v[j + off];
+            const float keep = upper ? v[j + off] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ unsigned tf32_hi(float v) { unsigned r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return r; }
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void fma2(f32x2 &d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
+__device__ __forceinline__ void item_fma2(const float *wimg, const float *xs, int lane, f32x2 (&acc)[4][4])
+{
+    float4 w[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const float4 *>(wimg + (r * 32 + lane) * 4);
+    const int sw = ((lane >> 2) & 1) * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float *xp = xs + (lane + 32 * i) * 8;
+        const float4 lo = *reinterpret_cast<const float4 *>(xp + sw);
+        const float4 hi = *reinterpret_cast<const float4 *>(xp + (4 - sw));
+        const f32x2 x0 = pack2(lo.x, lo.y), x1 = pack2(lo.z, lo.w), x2 = pack2(hi.x, hi.y), x3 = pack2(hi.z, hi.w);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float wv = (i == 0) ? w[r].x : (i == 1) ? w[r].y : (i == 2) ? w[r].z : w[r].w;
+            const f32x2 ww = pack2(wv, wv);
+            fma2(acc[r][0], ww, x0); fma2(acc[r][1], ww, x1); fma2(acc[r][2], ww, x2); fma2(acc[r][3], ww, x3);
+        }
+    }
+}
+__device__ __forceinline__ float reduce_nosel(f32x2 (&acc)[4][4])
+{
+    float v[32];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) unpack2(acc[r][j], v[r * 8 + 2 * j], v[r * 8 + 2 * j + 1]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+        for (int j = 0; j < off; ++j) v[j] = v[j] + __shfl_xor_sync(0xffffffffu, v[j + off], off);
+    }
+    return v[0];
+}
+// kind 0: FFMA items, weights from smem, one reduce per item | 1: same, 4 items per reduce
+// kind 2: FFMA, weights in registers (16 per item, 4 items) | 3: mma tf32 x1 | 4: 3xTF32 with on-the-fly split from smem fp32
+// kind 5: mma bf16 | 6: FFMA2 item + select-free reduce per item | 7: FFMA2 item without any reduce
+// kind 8: raw FFMA2 issue rate (16 independent accumulators, registers only) | 9: raw FFMA issue rate (32 accumulators)
+__global__ void __launch_bounds__(NT, 1) math(int kind, int iters, int nwarps, long long *cycles, float *sink)
+{
+    extern __shared__ float sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 16 * 512 + 4096 + 16 * 32; i += NT) sm[i] = 1e-3f * (float)((i * 37) % 101);
+    __syncthreads();
+    if (warp >= nwarps) return;
+    const float *W = sm, *X = sm + 16 * 512;
+    float *part = sm + 16 * 512 + 4096;
+    float res = 0.f;
+    const long long t0 = clock64();
+    if (kind == 0 || kind == 1) {
+        const int per = kind == 0 ? 1 : 4;
+        for (int it = 0; it < iters; it += per) {
+            float acc[4][8] = {};
+            for (int q = 0; q < per; ++q) item_fma(W + ((warp + it + q) & 15) * 512, X + ((it + q) & 3) * 1024, lane, acc);
+            part[warp * 32 + lane] = reduce_scatter32(acc, lane);
+            res += part[warp * 32 + (lane ^ 1)];
+        }
+    } else if (kind == 2) {
+        float w[4][16];
+        for (int q = 0; q < 4; ++q) for (int j = 0; j < 16; ++j) w[q][j] = W[((warp + q) & 15) * 512 + j * 32 + lane];
+        for (int it = 0; it < iters; it += 4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float acc[4][8] = {};
+                const int sw = ((lane >> 2) & 1) * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float *xp = X + q * 1024 + (lane + 32 * i) * 8;
+                    const float4 lo = *reinterpret_cast<const float4 *>(xp + sw);
+                    const float4 hi = *reinterpret_cast<const float4 *>(xp + (4 - sw));
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float wv = w[q][r * 4 + i];
+                        acc[r][0] = fmaf(wv, lo.x, acc[r][0]); acc[r][1] = fmaf(wv, lo.y, acc[r][1]);
+                        acc[r][2] = fmaf(wv, lo.z, acc[r][2]); acc[r][3] = fmaf(wv, lo.w, acc[r][3]);
+                        acc[r][4] = fmaf(wv, hi.x, acc[r][4]); acc[r][5] = fmaf(wv, hi.y, acc[r][5]);
+                        acc[r][6] = fmaf(wv, hi.z, acc[r][6]); acc[r][7] = fmaf(wv, hi.w, acc[r][7]);
+                    }
+                }
+                part[warp * 32 + lane] = reduce_scatter32(acc, lane);
+                res += part[warp * 32 + (lane ^ 1)];
+            }
+        }
+    } else if (kind == 6 || kind == 7) {
+        for (int it = 0; it < iters; ++it) {
+            f32x2 acc[4][4] = {};
+            item_fma2(W + ((warp + it) & 15) * 512, X + (it & 3) * 1024, lane, acc);
+            if (kind == 6) {
+                part[warp * 32 + lane] = reduce_nosel(acc);
+                res += part[warp * 32 + (lane ^ 1)];
+            } else {
+                float a, b;
+                for (int r = 0; r < 4; ++r) for (int j = 0; j < 4; ++j) { unpack2(acc[r][j], a, b); res += a + b; }
+            }
+        }
+    } else if (kind == 8) {
+        // `iters` counts groups of 64 FFMA2 (= one item's worth of math)
+        f32x2 acc[16];
+        for (int j = 0; j < 16; ++j) acc[j] = pack2((float)j, (float)lane);
+        f32x2 a = pack2(W[lane], W[lane]), b = pack2(X[lane], X[lane + 32]);
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) fma2(acc[j], a, b);
+        }
+        float x, y;
+        for (int j = 0; j < 16; ++j) { unpack2(acc[j], x, y); res += x + y; }
+    } else if (kind == 9) {
+        float acc[32];
+        for (int j = 0; j < 32; ++j) acc[j] = (float)(j + lane);
+        const float a = W[lane], b = X[lane];
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = fmaf(a, b + (float)q, acc[j]);
+        }
+        for (int j = 0; j < 32; ++j) res += acc[j];
+    } else if (kind == 3 || kind == 5) {
+        // `iters` counts 16x8x(8|16) MMAs per warp; 4 independent accumulator tiles
+        float d[4][4] = {};
+        unsigned a[4] = {__float_as_uint(W[lane]), __float_as_uint(W[lane + 32]), __float_as_uint(W[lane + 64]), __float_as_uint(W[lane + 96])};
+        unsigned b[2] = {__float_as_uint(X[lane]), __float_as_uint(X[lane + 32])};
+        for (int it = 0; it < iters; it += 4) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { if (kind == 3) mma_tf32(d[q], a, b); else mma_bf16(d[q], a, b); }
+        }
+        for (int q = 0; q < 4; ++q) res += d[q][0] + d[q][1] + d[q][2] + d[q][3];
+    } else if (kind == 4) {
+        // one "tile" = A 16x8 fp32 from smem (LDS.128, fragment order) split hi/lo, B 8x8 from smem split hi/lo, 3 MMAs.
+        // `iters` counts tiles per warp; 2 accumulator tiles (one per 16 rows), B shared by both.
+        float d[2][4] = {};
+        for (int it = 0; it < iters; it += 2) {
+            const float *xb = X + ((it >> 1) & 63) * 64;
+            const float b0 = xb[lane], b1 = xb[lane + 32];
+            unsigned bh[2] = {tf32_hi(b0), tf32_hi(b1)};
+            unsigned bl[2] = {__float_as_uint(b0 - __uint_as_float(bh[0])), __float_as_uint(b1 - __uint_as_float(bh[1]))};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 av = *reinterpret_cast<const float4 *>(W + (((it + q) * 128 + lane * 4) & 8191));
+                unsigned ah[4] = {tf32_hi(av.x), tf32_hi(av.y), tf32_hi(av.z), tf32_hi(av.w)};
+                unsigned al[4] = {__float_as_uint(av.x - __uint_as_float(ah[0])), __float_as_uint(av.y - __uint_as_float(ah[1])),
+                                  __float_as_uint(av.z - __uint_as_float(ah[2])), __float_as_uint(av.w - __uint_as_float(ah[3]))};
+                mma_tf32(d[q], al, bh);
+                mma_tf32(d[q], ah, bl);
+                mma_tf32(d[q], ah, bh);
+            }
+        }
+        for (int q = 0; q < 2; ++q) res += d[q][0] + d[q][1] + d[q][2] + d[q][3];
+    }
+    const long long t1 = clock64();
+    if (lane == 0) cycles[blockIdx.x * 16 + warp] = t1 - t0;
+    if (res == 1234.5f) sink[0] = res;
+}
+
+int main()
+{
+    unsigned *buf; unsigned long long *ll; int *errors; float *sink; long long *cycles;
+    const size_t bufbytes = (size_t)3 * 3 * 4 * 4096 * 4;
+    CK(cudaMalloc(&buf, bufbytes)); CK(cudaMalloc(&ll, 5 * 4096 * 8)); CK(cudaMalloc(&errors, 4)); CK(cudaMalloc(&sink, 16));
+    CK(cudaMalloc(&cycles, 148 * 16 * 8));
+    const int smem = 96 * 1024;
+    CK(cudaFuncSetAttribute(exch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(math, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    struct Case { int mode, lines, R; const char *name; };
+    const Case cases[] = {
+        {0, 256, 1, "LL pairs 32 KiB, 512 thr"},
+        {1, 128, 1, "poison 16 KiB, 512 thr, R=1"},
+        {1, 128, 2, "poison 16 KiB, 512 thr, R=2"},
+        {1, 128, 4, "poison 16 KiB, 512 thr, R=4"},
+        {1, 64, 1, "poison  8 KiB, 512 thr, R=1"},
+        {1, 32, 1, "poison  4 KiB, 512 thr, R=1"},
+        {1, 8, 1, "poison  1 KiB, 512 thr, R=1"},
+        {3, 128, 1, "poison 16 KiB, ONE team of 160 thr"},
+        {2, 128, 1, "poison 16 KiB, 3 teams x 160 thr (per round of 3 exchanges)"},
+        {2, 128, 2, "poison 16 KiB, 3 teams x 160 thr, R=2"},
+    };
+    for (const Case &c : cases) {
+        int iters = 2000;
+        float ms = 0;
+        int herr = 0;
+        for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaMemset(buf, 0xFF, bufbytes)); CK(cudaMemset(ll, 0, 5 * 4096 * 8)); CK(cudaMemset(errors, 0, 4));
+            int mode = c.mode, lines = c.lines, R = c.R;
+            void *args[] = {&mode, &iters, &lines, &R, &buf, &ll, &errors, &sink};
+            CK(cudaEventRecord(e0));
+            CK(cudaLaunchCooperativeKernel((void *)exch, dim3(128), dim3(NT), args, smem, 0));
+            CK(cudaEventRecord(e1));
+            CK(cudaDeviceSynchronize());
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            CK(cudaMemcpy(&herr, errors, 4, cudaMemcpyDeviceToHost));
+        }
+        printf("A  %-62s %.3f us/iter  errors %d\n", c.name, ms * 1000.f / iters, herr); fflush(stdout);
+    }
+    const char *knames[] = {"FFMA item (smem weights), reduce per item", "FFMA item (smem weights), reduce per 4 items",
+                            "FFMA item (register weights), reduce per item", "mma.sync m16n8k8 tf32 (1 MMA = 1024 MAC)",
+                            "3xTF32 tile: LDS A + split + 3 MMA (1 tile = 1024 MAC fp32-equivalent)", "mma.sync m16n8k16 bf16 (1 MMA = 2048 MAC)",
+                            "FFMA2 item (smem weights), select-free reduce per item", "FFMA2 item (smem weights), no reduce",
+                            "raw FFMA2 x64 (registers only)", "raw FFMA x128 (registers only)"};
+    for (int kind = 0; kind < 10; ++kind)
+        for (int nw : {16, 8, 4, 1}) {
+            int iters = 4096;
+            for (int rep = 0; rep < 2; ++rep) {
+                math<<<128, NT, smem>>>(kind, iters, nw, cycles, sink);
+                CK(cudaDeviceSynchronize());
+            }
+            long long h[16];
+            CK(cudaMemcpy(h, cycles, sizeof h, cudaMemcpyDeviceToHost));
+            long long mx = 0;
+            for (int w = 0; w < nw; ++w) mx = h[w] > mx ? h[w] : mx;
+            const double per = (double)mx / iters;                 // cycles per warp-unit with nw warps sharing the SM
+            const double mac = ((kind <= 2 || kind >= 6) ? 4096.0 : kind == 5 ? 2048.0 : 1024.0) * nw / per;
+            printf("B  %-72s warps %2d: %8.1f cycles per unit per warp, %7.1f MAC/clk/SM\n", knames[kind], nw, per, mac); fflush(stdout);
+        }
+    return 0;
+}

@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 from expressive_speech_synthesis_research_b200 import WaveRNN  # noqa: E402
 from oracle import synth  # noqa: E402
 
-SLOTS = ["SA gather(logits)", "SA sample", "SA gru1+publish", "S2 gather(h1)", "S2 items", "S2 finalize",
+SLOTS = ["(unused)", "SA poll+sample", "SA gru1+publish", "S2 gather(h1)", "S2 items", "S2 finalize",
          "S3 gather(h2)", "S3 items", "S3 finalize", "S4 cond_visit", "S4 gather(y1)", "S4 items", "S4 finalize",
          "S5 gather(y2)", "S5 items", "S5 finalize", "prefetch mbar wait", "re-polls after prefetch (thread 0, count)",
          "re-polls direct (thread 0, count)", "gather: own chunks", "gather: barrier wait"]
@@ -24,7 +24,14 @@ def main():
     m.cuda()
     eng = m._engine(dev)
     S = 3000
-    for B in (8, 20):
+    cases = [(8, None, 0), (14, None, 0), (14, None, 4000), (14, None, 8000), (20, None, 0), (20, None, 3000), (20, None, 6000),
+             (20, None, 12000), (48, None, 6000), (64, None, 6000)]
+    for B, force, stagger in cases:
+        os.environ["WRNN_STAGGER_CYCLES"] = str(stagger)
+        if force is None:
+            os.environ.pop("WRNN_FORCE_TEAMS", None)
+        else:
+            os.environ["WRNN_FORCE_TEAMS"] = force
         L = S + 64
         mu = torch.rand(B * L, 80, device=dev)
         au = torch.randn(B * L, 128, device=dev)
@@ -34,7 +41,7 @@ def main():
             for _ in range(2):
                 m._run_folds(eng, dev, mu, au, starts, starts + L, S, None, 1, None, False)
             ms = eng.info().last_kernel_ms
-            print("B=%d G=%d profiling=%s: %.3f ms, %.2f us/step" % (B, (B + 7) // 8, prof, ms, ms * 1e3 / S))
+            print("B=%d G=%d teams<=%s stagger=%d profiling=%s: %.3f ms, %.2f us/step" % (B, (B + 7) // 8, force or "3", stagger, prof, ms, ms * 1e3 / S), flush=True)
         cyc = eng.stage_cycles().astype(np.float64) / S
         G = (B + 7) // 8
         tot = cyc[:, :16].sum(1)

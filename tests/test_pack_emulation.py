@@ -30,9 +30,14 @@ def pack(sd, mode):
 
 
 def item_rows(img, base, idx):
-    """item image [4 rows][32 lanes][4] -> [4][128] with k = lane + 32*i"""
+    """item image [4 slots][32 lanes][4] -> [4 rows][128] with k = lane + 32*i; slot s of lane l holds
+    row s ^ (l >> 3) (the per-lane permutation behind the kernel's select-free reduce-scatter)"""
     it = img[:, base + idx * ITEM: base + (idx + 1) * ITEM].reshape(NCTA, 4, 32, 4)
-    return it.transpose(0, 1, 3, 2).reshape(NCTA, 4, 128).astype(np.float64)
+    rows = np.empty_like(it)
+    lanes = np.arange(32)
+    for s in range(4):
+        rows[:, s ^ (lanes >> 3), lanes, :] = it[:, s, lanes, :]
+    return rows.transpose(0, 1, 3, 2).reshape(NCTA, 4, 128).astype(np.float64)
 
 
 def matrix(img, base, rg, nchunk=4):
