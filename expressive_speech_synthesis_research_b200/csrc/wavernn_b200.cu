@@ -361,6 +361,8 @@ static int32_t launch_chunk(wrnn_handle *h, KParams &p, cudaStream_t st, bool pr
     {
         const char *sg = getenv("WRNN_STAGGER_CYCLES");     // development knob
         p.stagger = sg ? atoi(sg) : 6000;
+        const char *pm = getenv("WRNN_POLL_MODE");
+        p.poll_mode = pm ? atoi(pm) : 0;
     }
     h->smem_bytes = smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, p.T, p.nbuf).total * (int)sizeof(float);
     h->last_teams = p.T;

@@ -101,6 +101,7 @@ struct KParams {
     int feat, auxw;                    // 80, 128
     int T, nbuf;                       // teams per CTA, conditioning staging buffers per team
     int stagger;                       // start-up delay per team index (cycles): breaks the lockstep of the teams
+    int poll_mode;                     // 1: one warp per team polls a sentinel pair per producer, the others wait at a barrier
     int group_fold0[MAXG], group_nf[MAXG];
     int probe_iters;
     long long *prof;                   // optional [NCTA][PROF_SLOTS] per-stage cycle counters (clock64, team 0 thread 0)
@@ -335,6 +336,27 @@ __device__ __forceinline__ void poll_timeout(Ctx &c)
     atomicExch(c.p->status, -4);
 }
 
+// Single-warp wait (poll_mode 1): the last warp of the team polls ONE sentinel pair per producer CTA (the last
+// pair that producer publishes) and the rest of the team sleeps at the barrier.  64x fewer requests hammer L2
+// while the producers are still computing, which shortens the round trip of the loads that matter.
+__device__ __forceinline__ void wait_ready(Ctx &c, const unsigned long long *first, int stride, int nprod, unsigned epoch)
+{
+    if (c.tw == c.nw - 1) {
+        for (int q = c.lane; q < nprod; q += 32) {
+            const unsigned long long *sp = first + (size_t)q * stride;
+            uint2 v = ld_pair(sp);
+            for (int spin = 0; v.y != epoch; ++spin) {
+                if (spin > POLL_CAP) {
+                    poll_timeout(c);
+                    break;
+                }
+                v = ld_pair(sp);
+            }
+        }
+    }
+    team_sync(c);
+}
+
 // LL gather of one exchanged vector (VEC {value, epoch} pairs, [k][8] in L2) into the team's staging
 // buffer.  Every thread polls 16-byte chunks (two pairs) in batches of four until both epochs match.
 // Team-uniform result: false = the watchdog fired somewhere in this team (the kernel then exits and the
@@ -344,6 +366,7 @@ __device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src
 {
     float *dst = c.stage;
     constexpr int NCH = VEC / 2;
+    if (c.p->poll_mode == 1) wait_ready(c, src + 31, 32, NCTA, epoch);
 #pragma unroll 1
     for (int base = c.ttid; base < NCH; base += 4 * c.nt) {
         uint4 v[4];
@@ -635,48 +658,52 @@ __device__ __forceinline__ void dump_logits(Ctx &c, int g, int s)
     }
 }
 
-// The items of a stage are dealt round-robin to the warps of the team; item i leaves its 4 x 8 partial sums
-// in part[i * 32 + lane] (lane = row * 8 + fold), and the finalize roles add the K chunks in a fixed order,
-// so the arithmetic does not depend on the team size.  One copy of the mat-vec code serves every stage
-// (the loop body must stay inside the instruction cache).
-//   stage 1 (S2, x H1): 28 items = 7 row groups {Wih2x r,z,n | Whh1 r,z,n | Wfc1x} x 4 K chunks
-//   stage 2 (S3, x H2): 16 items = {Wfc1x | Whh2 r,z,n} x 4
-//   stage 3 (S4):       4 items Wfc2x x Y1, then the 12 conditioning items
-//   stage 4 (S5, x Y2): rows5 items = rows5/4 row groups x 4
-__device__ __forceinline__ void run_items(Ctx &c, int stage, bool run_main, bool run_cond)
+// The mat-vec work of a stage is cut into UNITS dealt round-robin to the warps of the team.  A unit is one row
+// group (4 rows x 8 folds) times two consecutive 128-wide K chunks: two items accumulated in registers, ONE
+// reduce-scatter (the shuffles share the shared-memory pipe with the operand loads, so they are worth saving).
+// Unit u leaves its partial sums in part[u * 32 + lane] (lane = row * 8 + fold) and the finalize roles add the
+// two K halves in a fixed order, so the arithmetic does not depend on the team size.  One copy of the mat-vec
+// code serves every stage (the loop body must stay inside the instruction cache).
+//   stage 1 (S2, x H1): 14 units = 7 row groups {Wih2x r,z,n | Whh1 r,z,n | Wfc1x} x 2 K halves
+//   stage 2 (S3, x H2):  8 units = {Wfc1x | Whh2 r,z,n} x 2
+//   stage 3 (S4):        2 units Wfc2x x Y1, then 8 conditioning units:
+//                        P1 r,z,n (item 0,1,2; chunk A) | P2 r,z,n (items 3+2q, 4+2q; chunks A,B) | P3 (9,10; A,B) | P4 (11; B)
+//   stage 4 (S5, x Y2): rows5/2 units = rows5/4 row groups x 2
+__device__ __forceinline__ void run_units(Ctx &c, int stage, bool run_main, bool run_cond)
 {
     const int rows5 = c.p->rows5;
-    const int n = stage == 1 ? 28 : stage == 4 ? rows5 : 16;
+    const int n = stage == 1 ? 14 : stage == 2 ? 8 : stage == 3 ? 10 : (rows5 >> 1);
     const float *W = c.sm + c.m.w;
 #pragma unroll 1
-    for (int i = c.tw; i < n; i += c.nw) {
+    for (int u = c.tw; u < n; u += c.nw) {
         f32x2 acc[4][4];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[r][j] = 0ull;
-        const int kc = i & 3;
-        if (stage == 3 && i >= 4) {
+        if (stage == 3 && u >= 2) {
             if (!run_cond) continue;
-            const int it = i - 4;
-            const int chunk = (it < 3) ? 0 : (it < 9) ? ((it - 3) & 1) : (it == 9) ? 0 : 1;
-            item_fma_cond(W + w_mc(rows5) + it * ITEM, c.cst + (c.cond_visit % c.p->nbuf) * (BT * CROW), chunk * 128, c.lane, acc);
+            const int cu = u - 2;
+            const int it0 = cu < 3 ? cu : cu < 6 ? 3 + 2 * (cu - 3) : cu == 6 ? 9 : 11;
+            const int nit = (cu < 3 || cu == 7) ? 1 : 2;
+            const int chunk0 = cu == 7 ? 1 : 0;
+            const float *cst = c.cst + (c.cond_visit % c.p->nbuf) * (BT * CROW);
+#pragma unroll 1
+            for (int q = 0; q < nit; ++q) item_fma_cond(W + w_mc(rows5) + (it0 + q) * ITEM, cst, (chunk0 + q) * 128, c.lane, acc);
         } else {
             if (!run_main) continue;
-            const int woff = stage == 1 ? (i < 24 ? W_M2 + i * ITEM : W_M3 + kc * ITEM)
-                           : stage == 2 ? W_M3 + i * ITEM
-                           : stage == 3 ? W_M4 + i * ITEM
-                                        : W_M5 + i * ITEM;
-            item_fma(W + woff, c.stage + kc * 128 * BT, c.lane, acc);
+            const int rg = u >> 1, h = u & 1;
+            const int woff = stage == 1 ? (rg < 6 ? W_M2 + (rg * 4 + 2 * h) * ITEM : W_M3 + 2 * h * ITEM)
+                           : stage == 2 ? W_M3 + (rg * 4 + 2 * h) * ITEM
+                           : stage == 3 ? W_M4 + 2 * h * ITEM
+                                        : W_M5 + (rg * 4 + 2 * h) * ITEM;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) item_fma(W + woff + q * ITEM, c.stage + (2 * h + q) * 128 * BT, c.lane, acc);
         }
-        c.part[i * 32 + c.lane] = reduce_scatter32(acc);
+        c.part[u * 32 + c.lane] = reduce_scatter32(acc);
     }
 }
-__device__ __forceinline__ float sum4(const float *part, int rg, int lane)
-{
-    const float *q = part + rg * 128 + lane;
-    return (q[0] + q[32]) + (q[64] + q[96]);
-}
+__device__ __forceinline__ float sum2(const float *part, int rg, int lane) { return part[rg * 64 + lane] + part[rg * 64 + 32 + lane]; }
 
 // One visit: stage `stage` of step t for group g.  Returns false when the watchdog fired (team-uniform).
 template <bool PROF>
@@ -701,7 +728,10 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
         if (t > 0) {
             // sample step t-1 from its logits (epoch t).  The barrier orders the draws committed at S4 (CTAs that
             // do not produce logits come here straight from S4's finalize).
-            team_sync(c);
+            if (p.poll_mode == 1)
+                wait_ready(c, xb + XB_LG + (size_t)(BT - 1) * (p.rows5 * p.nprod5) + (p.rows5 - 1), p.rows5, p.nprod5, (unsigned)t);
+            else
+                team_sync(c);
             if (p.mode != 0) sample_mol(c, g, t - 1, (unsigned)t);
             else switch (p.C) {
                 case 1024: sample_raw<32>(c, g, t - 1, (unsigned)t); break;
@@ -724,7 +754,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
             if (!gather_vec<PROF>(c, xb + (stage - 1) * VEC, epoch)) return false;   // H1 | H2 | Y1 | Y2
             tick<PROF>(c, 3 * stage + (stage >= 3 ? 1 : 0));
         }
-        run_items(c, stage, !warm, t + 1 < S);
+        run_units(c, stage, !warm, t + 1 < S);
         team_sync(c);
         tick<PROF>(c, 3 * stage + 1 + (stage >= 3 ? 1 : 0));
         if (stage == 3) {
@@ -750,7 +780,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     gi[q] = pg[P + q * 32 + lane] + x * sv[SU + q * 4 + u] + sv[SB + q * 4 + u];
-                    if (stage == 1) gi[q] += sum4(part, q, lane);
+                    if (stage == 1) gi[q] += sum2(part, q, lane);
                 }
                 const float r = sigmoidf_(gi[0] + pg[GH + lane]);
                 const float z = sigmoidf_(gi[1] + pg[GH + 32 + lane]);
@@ -761,40 +791,40 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
                 tick<PROF>(c, stage == 0 ? 2 : 5);
             } else if (role <= 3) {
                 const int q = role - 1;   // gh1 of the NEXT step: Whh1 . h1_t + b_hh1
-                pg[PG_GH1 + q * 32 + lane] = sum4(part, 3 + q, lane) + sv[SV_BHH1 + q * 4 + (lane >> 3)];
+                pg[PG_GH1 + q * 32 + lane] = sum2(part, 3 + q, lane) + sv[SV_BHH1 + q * 4 + (lane >> 3)];
             } else
-                pg[PG_F1 + lane] = sum4(part, 6, lane);                                    // Wfc1x . h1_t
+                pg[PG_F1 + lane] = sum2(part, 6, lane);                                    // Wfc1x . h1_t
         } else if (stage == 2) {
             // S3: fc1 (h2 part + saved h1 part); gh2 of the next step
             if (role == 0) {
                 const int u = lane >> 3, f = lane & 7;
-                float y = (sum4(part, 0, lane) + pg[PG_F1 + lane]) + pg[PG_P3 + lane] + pg[PG_X + f] * sv[SV_U3 + u] + sv[SV_B3 + u];
+                float y = (sum2(part, 0, lane) + pg[PG_F1 + lane]) + pg[PG_P3 + lane] + pg[PG_X + f] * sv[SV_U3 + u] + sv[SV_B3 + u];
                 y = fmaxf(y, 0.f);
                 publish_line(xb + XB_Y1, c.cta, lane, y, epoch);
                 tick<PROF>(c, 8);
             } else {
                 const int q = role - 1;
-                pg[PG_GH2 + q * 32 + lane] = sum4(part, 1 + q, lane) + sv[SV_BHH2 + q * 4 + (lane >> 3)];
+                pg[PG_GH2 + q * 32 + lane] = sum2(part, 1 + q, lane) + sv[SV_BHH2 + q * 4 + (lane >> 3)];
             }
         } else if (stage == 3) {
             // S4: fc2; conditioning projections of step t+1
-            // cond item order: 0-2 P1 (chunk A) | 3-8 P2 (rg*2 + chunk) | 9,10 P3 (A,B) | 11 P4 (B); part slot = 4 + item
+            // conditioning units leave P1 r,z,n | P2 r,z,n | P3 | P4 in part slots 2..9
             if (role == 0) {
                 if (!warm) {
-                    float y = sum4(part, 0, lane) + pg[PG_P4 + lane] + sv[SV_B4 + (lane >> 3)];
+                    float y = sum2(part, 0, lane) + pg[PG_P4 + lane] + sv[SV_B4 + (lane >> 3)];
                     y = fmaxf(y, 0.f);
                     publish_line(xb + XB_Y2, c.cta, lane, y, epoch);
                     tick<PROF>(c, 12);
                 }
-                if (t + 1 < S) pg[PG_P4 + lane] = part[(4 + 11) * 32 + lane];
+                if (t + 1 < S) pg[PG_P4 + lane] = part[9 * 32 + lane];
             } else if (t + 1 < S) {
-                if (role <= 3) pg[PG_P1 + (role - 1) * 32 + lane] = part[(4 + (role - 1)) * 32 + lane];
-                else if (role <= 6) pg[PG_P2 + (role - 4) * 32 + lane] = part[(4 + 3 + 2 * (role - 4)) * 32 + lane] + part[(4 + 4 + 2 * (role - 4)) * 32 + lane];
-                else pg[PG_P3 + lane] = part[(4 + 9) * 32 + lane] + part[(4 + 10) * 32 + lane];
+                if (role <= 3) pg[PG_P1 + (role - 1) * 32 + lane] = part[(2 + (role - 1)) * 32 + lane];
+                else if (role <= 6) pg[PG_P2 + (role - 4) * 32 + lane] = part[(5 + (role - 4)) * 32 + lane];
+                else pg[PG_P3 + lane] = part[8 * 32 + lane];
             }
         } else {
             // S5: logits of this CTA's rows5 classes, published fold-major
-            const float v = sum4(part, role, lane) + sv[SV_B5 + role * 4 + (lane >> 3)];
+            const float v = sum2(part, role, lane) + sv[SV_B5 + role * 4 + (lane >> 3)];
             const int k = p.rows5 * c.cta + role * 4 + (lane >> 3);
             st_pair(xb + XB_LG + (size_t)(lane & 7) * (p.rows5 * p.nprod5) + k, v, epoch);
             tick<PROF>(c, 15);

@@ -24,10 +24,10 @@ def main():
     m.cuda()
     eng = m._engine(dev)
     S = 3000
-    cases = [(8, None, 0), (14, None, 0), (14, None, 4000), (14, None, 8000), (20, None, 0), (20, None, 3000), (20, None, 6000),
-             (20, None, 12000), (48, None, 6000), (64, None, 6000)]
+    cases = [(8, None, 0), (8, None, -1), (14, None, 0), (14, None, -1), (20, None, 0), (20, None, -1), (20, "1", -1), (64, None, -1)]
     for B, force, stagger in cases:
-        os.environ["WRNN_STAGGER_CYCLES"] = str(stagger)
+        os.environ["WRNN_POLL_MODE"] = "1" if stagger < 0 else "0"
+        os.environ["WRNN_STAGGER_CYCLES"] = str(max(stagger, 0))
         if force is None:
             os.environ.pop("WRNN_FORCE_TEAMS", None)
         else:
