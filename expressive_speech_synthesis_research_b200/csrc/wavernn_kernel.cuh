@@ -174,6 +174,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k)
     return c;
 }
 __device__ __forceinline__ float u01(unsigned x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+// uniform j of (step, fold b): word j & 3 of Philox(counter = {step, b, j >> 2, 0}, key = seed).  Out of line: one
+// warp per visit needs it and the step loop has to stay small.
+__device__ __noinline__ float philox_uniform(unsigned long long seed, int step, int b, int j)
+{
+    const uint4 r = philox4x32_10(make_uint4((unsigned)step, (unsigned)b, (unsigned)(j >> 2), 0u), make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    return u01(((j & 3) == 0) ? r.x : ((j & 3) == 1) ? r.y : ((j & 3) == 2) ? r.z : r.w);
+}
 
 constexpr int POLL_CAP = 1 << 22;    // watchdog: ~1 s of polling
 
@@ -306,7 +313,8 @@ struct Ctx {
     float *stage, *part, *cst;        // this team's staging buffers
     uint64_t *mbar;                   // this team's two conditioning mbarriers
     int *abort_flag;
-    int cond_visit;      // running count of this team's conditioning visits (selects staging buffer / parity)
+    int cv_buf, cv_par;  // conditioning visit being consumed: staging buffer index, mbarrier phase parity
+    int is_g, is_step, is_buf;   // next conditioning visit to issue (maintained by the issuing warp only)
     long long tprev;     // profiling: last timestamp (team 0, thread 0)
     float du[3], dfx;    // draws fetched by draws_issue, waiting for draws_commit (last warp of the team)
 };
@@ -367,6 +375,7 @@ __device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src
     float *dst = c.stage;
     constexpr int NCH = VEC / 2;
     if (c.p->poll_mode == 1) wait_ready(c, src + 31, 32, NCTA, epoch);
+    if (c.p->poll_mode == 2) team_sync(c);       // nobody polls before this CTA has published its own line
 #pragma unroll 1
     for (int base = c.ttid; base < NCH; base += 4 * c.nt) {
         uint4 v[4];
@@ -405,17 +414,31 @@ __device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src
     return *c.abort_flag == 0;
 }
 
-// Conditioning visit v of this team is (group team + T * (v % ng), step v / ng).
-// Issue its TMA row copies into staging buffer v % nbuf.  Called by ALL lanes of one warp: lane f < 8
-// copies fold f's two rows (mel 320 B + aux 512 B).  Rows past fold_limit are the fold padding (zeros,
-// fatchord_version.py:306-309): they are not copied, the warp zero-fills them instead.
-__device__ __forceinline__ void cond_issue(Ctx &c, int v)
+// Cold path of cond_issue: zero the staging rows of folds that have run past their conditioning (fold padding,
+// fatchord_version.py:306-309) or do not exist.  Kept out of line so the step loop stays small.
+__device__ __noinline__ void cond_zero_rows(float *buf, unsigned mask, int lane)
+{
+    for (int ff = 0; ff < BT; ++ff)
+        if (!((mask >> ff) & 1))
+            for (int i = lane; i < CROW; i += 32) buf[ff * CROW + i] = 0.f;
+}
+
+// The conditioning visits of a team run over (step, its groups) in that order; visit number v uses staging
+// buffer v % nbuf.  Issue the TMA row copies of the next visit (is_g, is_step) and advance.  Called by ALL lanes
+// of the team's last warp: lane f < 8 copies fold f's two rows (mel 320 B + aux 512 B).
+__device__ __forceinline__ void cond_issue_next(Ctx &c)
 {
     const KParams &p = *c.p;
-    const int g = c.team + p.T * (v % c.ng), step = v / c.ng;
+    const int g = c.is_g, step = c.is_step, b = c.is_buf;
+    c.is_g += p.T;
+    if (c.is_g >= p.G) {
+        c.is_g = c.team;
+        c.is_step += 1;
+    }
+    c.is_buf = (b + 1 == p.nbuf) ? 0 : b + 1;
     if (step >= p.S) return;
-    float *buf = c.cst + (v % p.nbuf) * (BT * CROW);
-    uint64_t *bar = c.mbar + (v % p.nbuf);
+    float *buf = c.cst + b * (BT * CROW);
+    uint64_t *bar = c.mbar + b;
     const int f = c.lane;
     bool valid = false;
     long long row = 0;
@@ -425,11 +448,7 @@ __device__ __forceinline__ void cond_issue(Ctx &c, int v)
         valid = row < fs[MAXG * BT + g * BT + f];
     }
     const unsigned m = __ballot_sync(0xffffffffu, valid) & 0xffu;
-    if (m != 0xffu) {
-        for (int ff = 0; ff < BT; ++ff)
-            if (!((m >> ff) & 1))
-                for (int i = c.lane; i < CROW; i += 32) buf[ff * CROW + i] = 0.f;
-    }
+    if (m != 0xffu) cond_zero_rows(buf, m, c.lane);
     // the staging buffer was last read through the generic proxy (work items, before the team barrier)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
@@ -441,15 +460,11 @@ __device__ __forceinline__ void cond_issue(Ctx &c, int v)
     }
 }
 
-// Wait until the conditioning rows of this team's next visit have landed.  All threads of the team.
+// Wait until the conditioning rows of the visit being consumed have landed.  All threads of the team.
 __device__ __forceinline__ void cond_wait(Ctx &c)
 {
-    const KParams &p = *c.p;
-    const int v = c.cond_visit;
-    if (v / c.ng >= p.S) return;
-    uint64_t *bar = c.mbar + (v % p.nbuf);
-    const unsigned parity = (unsigned)((v / p.nbuf) & 1);
-    while (!mbar_try_wait(bar, parity)) {
+    uint64_t *bar = c.mbar + c.cv_buf;
+    while (!mbar_try_wait(bar, (unsigned)c.cv_par)) {
     }
 }
 
@@ -468,13 +483,7 @@ __device__ __forceinline__ void draws_issue(Ctx &c, int g, int step)
             const int f = i / nu, j = i - f * nu;
             if (f < p.group_nf[g]) {
                 const int b = p.group_fold0[g] + f;
-                if (p.uniforms) u = p.uniforms[((size_t)step * p.B + b) * nu + j];
-                else {
-                    uint4 r = philox4x32_10(make_uint4((unsigned)step, (unsigned)b, (unsigned)(j >> 2), 0u),
-                                            make_uint2((unsigned)p.seed, (unsigned)(p.seed >> 32)));
-                    const unsigned x = ((j & 3) == 0) ? r.x : ((j & 3) == 1) ? r.y : ((j & 3) == 2) ? r.z : r.w;
-                    u = u01(x);
-                }
+                u = p.uniforms ? p.uniforms[((size_t)step * p.B + b) * nu + j] : philox_uniform(p.seed, step, b, j);
             }
         }
         c.du[q] = u;
@@ -687,7 +696,7 @@ __device__ __forceinline__ void run_units(Ctx &c, int stage, bool run_main, bool
             const int it0 = cu < 3 ? cu : cu < 6 ? 3 + 2 * (cu - 3) : cu == 6 ? 9 : 11;
             const int nit = (cu < 3 || cu == 7) ? 1 : 2;
             const int chunk0 = cu == 7 ? 1 : 0;
-            const float *cst = c.cst + (c.cond_visit % c.p->nbuf) * (BT * CROW);
+            const float *cst = c.cst + c.cv_buf * (BT * CROW);
 #pragma unroll 1
             for (int q = 0; q < nit; ++q) item_fma_cond(W + w_mc(rows5) + (it0 + q) * ITEM, cst, (chunk0 + q) * 128, c.lane, acc);
         } else {
@@ -720,7 +729,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
 
     if (warm) team_sync(c);                              // no gather barrier in the warm-up pass: part is reused
     if (stage == 3) {
-        cond_wait(c);                                    // conditioning rows of step t+1 of this group
+        if (t + 1 < S) cond_wait(c);                     // conditioning rows of step t+1 of this group
         tick<PROF>(c, 9);
         if (tw == nw - 1 && !warm) draws_issue(c, g, t); // draws consumed by the sample of step t (at SA of t+1)
     }
@@ -759,8 +768,11 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
         tick<PROF>(c, 3 * stage + 1 + (stage >= 3 ? 1 : 0));
         if (stage == 3) {
             // the staging buffer of this conditioning visit is free again: refill it for visit v + nbuf
-            if (tw == nw - 1) cond_issue(c, c.cond_visit + p.nbuf);
-            c.cond_visit += 1;
+            if (tw == nw - 1) cond_issue_next(c);
+            if (++c.cv_buf == p.nbuf) {
+                c.cv_buf = 0;
+                c.cv_par ^= 1;
+            }
         }
     }
 
@@ -852,10 +864,12 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
     c.team = c.warp / c.nw;
     c.tw = c.warp - c.team * c.nw;
     c.ttid = c.tid - c.team * c.nt;
-    c.cond_visit = 0;
+    c.cv_buf = c.cv_par = 0;
+    c.is_step = c.is_buf = 0;
     c.tprev = 0;
     const bool member = c.team < p.T;
     c.ng = member ? (p.G - c.team + p.T - 1) / p.T : 0;
+    c.is_g = c.team;
     {
         float *tb = sm + c.m.team0 + (member ? c.team : 0) * c.m.team_stride;
         c.stage = tb + c.m.t_stage;
@@ -901,7 +915,7 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
     }
     if (!member) return;                         // spare warp (3 teams x 5 warps)
     if (c.tw == c.nw - 1)
-        for (int v = 0; v < p.nbuf; ++v) cond_issue(c, v);
+        for (int v = 0; v < p.nbuf; ++v) cond_issue_next(c);
 
     if (c.team > 0 && p.stagger > 0) {
         // Teams that start together stay in lockstep (all in their mat-vecs, then all waiting on an exchange);

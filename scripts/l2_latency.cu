@@ -25,6 +25,35 @@ template <int F> __global__ void chase(const unsigned *buf, int n, long long *ou
     if (threadIdx.x == 0) { out[0] = (t1 - t0) / n; out[1] = idx; }
 }
 // ping-pong between CTA 0 and CTA `peer`: one-way latency = total / (2 n)
+template <int ST> __device__ __forceinline__ void st(unsigned *p, unsigned v)
+{
+    if (ST == 0) asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    if (ST == 1) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    if (ST == 2) asm volatile("st.global.cg.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    if (ST == 3) asm volatile("st.global.wt.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    if (ST == 4) { unsigned o; asm volatile("atom.global.exch.b32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory"); }
+    if (ST == 5) asm volatile("red.global.max.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    if (ST == 6) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+template <int ST> __global__ void pingpong2(unsigned *flags, int n, int peer, long long *out)
+{
+    if (threadIdx.x != 0) return;
+    const int me = blockIdx.x;
+    if (me != 0 && me != peer) return;
+    unsigned *mine = flags + (me == 0 ? 0 : 32), *other = flags + (me == 0 ? 32 : 0);
+    long long t0 = clock64();
+    for (int i = 1; i <= n; ++i) {
+        if (me == 0) {
+            st<ST>(other, (unsigned)i);
+            while (ld<0>(mine) != (unsigned)i) { }
+        } else {
+            while (ld<0>(mine) != (unsigned)i) { }
+            st<ST>(other, (unsigned)i);
+        }
+    }
+    long long t1 = clock64();
+    if (me == 0) out[0] = (t1 - t0) / n;
+}
 template <int F> __global__ void pingpong(unsigned *flags, int n, int peer, long long *out)
 {
     if (threadIdx.x != 0) return;
@@ -60,5 +89,9 @@ int main()
 #define PP(F, peer) CK(cudaMemset(flags, 0, 256)); pingpong<F><<<148, 32>>>(flags, 2000, peer, out); CK(cudaDeviceSynchronize()); \
     CK(cudaMemcpy(r, out, 8, cudaMemcpyDeviceToHost)); printf("ping-pong %-16s CTA0<->CTA%-3d %lld cycles per round trip (2 stores + 2 successful polls)\n", names[F], peer, r[0]);
     PP(0, 1) PP(0, 74) PP(0, 147) PP(1, 1) PP(1, 74) PP(1, 147) PP(2, 74) PP(4, 74)
+    const char *sn[] = {"st.volatile", "st.relaxed.gpu", "st.global.cg", "st.global.wt", "atom.exch", "red.max", "st.release.gpu"};
+#define PP2(ST) CK(cudaMemset(flags, 0, 256)); pingpong2<ST><<<148, 32>>>(flags, 2000, 74, out); CK(cudaDeviceSynchronize()); \
+    CK(cudaMemcpy(r, out, 8, cudaMemcpyDeviceToHost)); printf("ping-pong store %-16s + ld.volatile: %lld cycles per round trip\n", sn[ST], r[0]);
+    PP2(0) PP2(1) PP2(2) PP2(3) PP2(4) PP2(5) PP2(6)
     return 0;
 }

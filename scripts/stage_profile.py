@@ -24,9 +24,9 @@ def main():
     m.cuda()
     eng = m._engine(dev)
     S = 3000
-    cases = [(8, None, 0), (8, None, -1), (14, None, 0), (14, None, -1), (20, None, 0), (20, None, -1), (20, "1", -1), (64, None, -1)]
+    cases = [(8, None, 0), (8, None, -2), (14, None, -2), (20, None, 0), (20, None, -2), (64, None, -2)]
     for B, force, stagger in cases:
-        os.environ["WRNN_POLL_MODE"] = "1" if stagger < 0 else "0"
+        os.environ["WRNN_POLL_MODE"] = str(-stagger) if stagger < 0 else "0"
         os.environ["WRNN_STAGGER_CYCLES"] = str(max(stagger, 0))
         if force is None:
             os.environ.pop("WRNN_FORCE_TEAMS", None)
