@@ -39,7 +39,7 @@ constexpr int ITEM = 4 * 32 * 4;  // floats of one weight item image: 4 rows x 1
 constexpr int NEXCH = 5;
 constexpr int CROW = 208;         // conditioning floats per fold-step: 80 mel + 4*32 aux
 constexpr int COND_ITEMS = 12;
-constexpr int PART_FLOATS = 32 * 32;   // per-team partial sums: up to 32 items x (4 rows x 8 folds)
+constexpr int PART_FLOATS = 24 * 32;   // per-team partial sums: 16 critical item slots + 8 deferred unit slots, x (4 rows x 8 folds)
 
 // ---- per-CTA weight image (floats) --------------------------------------------------------
 // An item image is [4 slots][32 lanes] float4: slot r of lane l holds W[row r ^ (l >> 3)][kbase + l + 32 i], i = 0..3
@@ -667,52 +667,110 @@ __device__ __forceinline__ void dump_logits(Ctx &c, int g, int s)
     }
 }
 
-// The mat-vec work of a stage is cut into UNITS dealt round-robin to the warps of the team.  A unit is one row
-// group (4 rows x 8 folds) times two consecutive 128-wide K chunks: two items accumulated in registers, ONE
-// reduce-scatter (the shuffles share the shared-memory pipe with the operand loads, so they are worth saving).
-// Unit u leaves its partial sums in part[u * 32 + lane] (lane = row * 8 + fold) and the finalize roles add the
-// two K halves in a fixed order, so the arithmetic does not depend on the team size.  One copy of the mat-vec
-// code serves every stage (the loop body must stay inside the instruction cache).
-//   stage 1 (S2, x H1): 14 units = 7 row groups {Wih2x r,z,n | Whh1 r,z,n | Wfc1x} x 2 K halves
-//   stage 2 (S3, x H2):  8 units = {Wfc1x | Whh2 r,z,n} x 2
-//   stage 3 (S4):        2 units Wfc2x x Y1, then 8 conditioning units:
-//                        P1 r,z,n (item 0,1,2; chunk A) | P2 r,z,n (items 3+2q, 4+2q; chunks A,B) | P3 (9,10; A,B) | P4 (11; B)
-//   stage 4 (S5, x Y2): rows5/2 units = rows5/4 row groups x 2
-__device__ __forceinline__ void run_units(Ctx &c, int stage, bool run_main, bool run_cond)
+// The mat-vec work of a stage runs in two phases.
+//  CRITICAL: only what the value published by this stage needs, cut into single ITEMS (4 rows x 8 folds x 128 k,
+//    one reduce-scatter each) so that as many warps as possible shorten the dependent chain:
+//      S2 12 items Wih2x{r,z,n} x 4 K chunks | S3 4 items Wfc1x | S4 4 items Wfc2x | S5 rows5 items Wfc3
+//    Item i leaves its partial sums in part[i * 32 + lane] (lane = row * 8 + fold); the finalize adds the four
+//    K chunks in a fixed order.
+//  DEFERRED: everything whose result is only needed later, run AFTER the stage has published (i.e. inside the
+//    exchange latency), cut into UNITS of two consecutive K chunks with ONE reduce-scatter (the shuffles share
+//    the shared-memory pipe with the operand loads, so they are worth saving):
+//      S2 8 units {Whh1 r,z,n | Wfc1x} x 2 K halves (next step's gh1, this step's fc1 input)
+//      S3 6 units Whh2{r,z,n} x 2 (next step's gh2)
+//      S4 8 conditioning units: P1 r,z,n (item 0,1,2; chunk A) | P2 r,z,n (items 3+2q, 4+2q; A,B) | P3 (9,10; A,B) | P4 (11; B)
+//    Unit u leaves its sums in part[(DEF0 + u) * 32 + lane].
+// Work is dealt round-robin to the warps of the team and combined in a fixed order, so the arithmetic does not
+// depend on the team size.  One copy of the mat-vec code serves every stage (instruction cache).
+constexpr int DEF0 = 16;    // first deferred slot of the partial-sum buffer
+
+__device__ __forceinline__ void zero_acc(f32x2 (&acc)[4][4])
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[r][j] = 0ull;
+}
+
+__device__ __forceinline__ void run_critical(Ctx &c, int stage)
 {
     const int rows5 = c.p->rows5;
-    const int n = stage == 1 ? 14 : stage == 2 ? 8 : stage == 3 ? 10 : (rows5 >> 1);
-    const float *W = c.sm + c.m.w;
+    const int n = stage == 1 ? 12 : stage == 4 ? rows5 : 4;
+    const int woff = stage == 1 ? W_M2 : stage == 2 ? W_M3 : stage == 3 ? W_M4 : W_M5;
+    const float *W = c.sm + c.m.w + woff;
 #pragma unroll 1
-    for (int u = c.tw; u < n; u += c.nw) {
+    for (int i = c.tw; i < n; i += c.nw) {
         f32x2 acc[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[r][j] = 0ull;
-        if (stage == 3 && u >= 2) {
-            if (!run_cond) continue;
-            const int cu = u - 2;
-            const int it0 = cu < 3 ? cu : cu < 6 ? 3 + 2 * (cu - 3) : cu == 6 ? 9 : 11;
-            const int nit = (cu < 3 || cu == 7) ? 1 : 2;
-            const int chunk0 = cu == 7 ? 1 : 0;
+        zero_acc(acc);
+        item_fma(W + i * ITEM, c.stage + (i & 3) * 128 * BT, c.lane, acc);
+        c.part[i * 32 + c.lane] = reduce_scatter32(acc);
+    }
+}
+
+__device__ __forceinline__ void run_deferred(Ctx &c, int stage)
+{
+    const int rows5 = c.p->rows5;
+    const int n = stage == 1 ? 8 : stage == 2 ? 6 : 8;
+    const float *W = c.sm + c.m.w;
+    // deal from warp 1 on: warp 0 is busy with the pointwise math + publish of this stage
+    int first = c.tw - 1;
+    if (first < 0) first += c.nw;
+#pragma unroll 1
+    for (int u = first; u < n; u += c.nw) {
+        f32x2 acc[4][4];
+        zero_acc(acc);
+        if (stage == 3) {
+            const int it0 = u < 3 ? u : u < 6 ? 3 + 2 * (u - 3) : u == 6 ? 9 : 11;
+            const int nit = (u < 3 || u == 7) ? 1 : 2;
+            const int chunk0 = u == 7 ? 1 : 0;
             const float *cst = c.cst + c.cv_buf * (BT * CROW);
 #pragma unroll 1
             for (int q = 0; q < nit; ++q) item_fma_cond(W + w_mc(rows5) + (it0 + q) * ITEM, cst, (chunk0 + q) * 128, c.lane, acc);
         } else {
-            if (!run_main) continue;
             const int rg = u >> 1, h = u & 1;
-            const int woff = stage == 1 ? (rg < 6 ? W_M2 + (rg * 4 + 2 * h) * ITEM : W_M3 + 2 * h * ITEM)
-                           : stage == 2 ? W_M3 + (rg * 4 + 2 * h) * ITEM
-                           : stage == 3 ? W_M4 + 2 * h * ITEM
-                                        : W_M5 + (rg * 4 + 2 * h) * ITEM;
+            // S2: row groups 3..5 of M2 (Whh1), then Wfc1x = row group 0 of M3;  S3: row groups 1..3 of M3 (Whh2)
+            const int woff = stage == 1 ? (rg < 3 ? W_M2 + ((3 + rg) * 4 + 2 * h) * ITEM : W_M3 + 2 * h * ITEM)
+                                        : W_M3 + ((1 + rg) * 4 + 2 * h) * ITEM;
 #pragma unroll
             for (int q = 0; q < 2; ++q) item_fma(W + woff + q * ITEM, c.stage + (2 * h + q) * 128 * BT, c.lane, acc);
         }
-        c.part[u * 32 + c.lane] = reduce_scatter32(acc);
+        c.part[(DEF0 + u) * 32 + c.lane] = reduce_scatter32(acc);
     }
 }
-__device__ __forceinline__ float sum2(const float *part, int rg, int lane) { return part[rg * 64 + lane] + part[rg * 64 + 32 + lane]; }
+__device__ __forceinline__ float sum4(const float *part, int rg, int lane)
+{
+    const float *q = part + rg * 128 + lane;
+    return (q[0] + q[32]) + (q[64] + q[96]);
+}
+__device__ __forceinline__ float sum2d(const float *part, int pair, int lane)      // deferred units 2*pair, 2*pair+1
+{
+    return part[(DEF0 + 2 * pair) * 32 + lane] + part[(DEF0 + 2 * pair + 1) * 32 + lane];
+}
+
+// GRU cell of this CTA's 4 units x 8 folds (torch gate order r, z, n) + publish of the new state.  One warp.
+// which = 0: rnn1 (input side folded into P1; gate pre-activations need no mat-vec), 1: rnn2 (input side =
+// Wih2x . h1 from the critical items + P2).
+template <bool PROF>
+__device__ __forceinline__ void gru_publish(Ctx &c, float *pg, unsigned long long *xb, const float *sv, const float *part, int which, unsigned epoch)
+{
+    const int lane = c.lane, u = lane >> 3, f = lane & 7;
+    const float x = pg[PG_X + f];
+    const int P = which == 0 ? PG_P1 : PG_P2, GH = which == 0 ? PG_GH1 : PG_GH2, H = which == 0 ? PG_H1 : PG_H2;
+    const int SU = which == 0 ? SV_U1 : SV_U2, SB = which == 0 ? SV_B1 : SV_B2;
+    float gi[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        gi[q] = pg[P + q * 32 + lane] + x * sv[SU + q * 4 + u] + sv[SB + q * 4 + u];
+        if (which == 1) gi[q] += sum4(part, q, lane);
+    }
+    const float r = sigmoidf_(gi[0] + pg[GH + lane]);
+    const float z = sigmoidf_(gi[1] + pg[GH + 32 + lane]);
+    const float n = tanhf(gi[2] + r * pg[GH + 64 + lane]);
+    const float h = (1.0f - z) * n + z * pg[H + lane];
+    pg[H + lane] = h;
+    publish_line(xb + (which == 0 ? XB_H1 : XB_H2), c.cta, lane, h, epoch);
+    tick<PROF>(c, which == 0 ? 2 : 5);
+}
 
 // One visit: stage `stage` of step t for group g.  Returns false when the watchdog fired (team-uniform).
 template <bool PROF>
@@ -728,11 +786,6 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     const bool warm = t < 0;
 
     if (warm) team_sync(c);                              // no gather barrier in the warm-up pass: part is reused
-    if (stage == 3) {
-        if (t + 1 < S) cond_wait(c);                     // conditioning rows of step t+1 of this group
-        tick<PROF>(c, 9);
-        if (tw == nw - 1 && !warm) draws_issue(c, g, t); // draws consumed by the sample of step t (at SA of t+1)
-    }
     if (stage == 0) {
         if (t > 0) {
             // sample step t-1 from its logits (epoch t).  The barrier orders the draws committed at S4 (CTAs that
@@ -758,88 +811,78 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
             }
         }
         if (t == S) return true;
-    } else {
-        if (!warm) {
-            if (!gather_vec<PROF>(c, xb + (stage - 1) * VEC, epoch)) return false;   // H1 | H2 | Y1 | Y2
-            tick<PROF>(c, 3 * stage + (stage >= 3 ? 1 : 0));
-        }
-        run_units(c, stage, !warm, t + 1 < S);
-        team_sync(c);
-        tick<PROF>(c, 3 * stage + 1 + (stage >= 3 ? 1 : 0));
-        if (stage == 3) {
-            // the staging buffer of this conditioning visit is free again: refill it for visit v + nbuf
-            if (tw == nw - 1) cond_issue_next(c);
-            if (++c.cv_buf == p.nbuf) {
-                c.cv_buf = 0;
-                c.cv_par ^= 1;
-            }
-        }
     }
 
-    // ---- finalize: pointwise math of this CTA's 4 units x 8 folds, publish ----------------------
-    const int nroles = stage == 0 ? 1 : stage == 1 ? 5 : stage == 2 ? 4 : stage == 3 ? 8 : (p.rows5 >> 2);
-#pragma unroll 1
-    for (int role = tw; role < nroles; role += nw) {
+    // stages 1..4: gather + critical items, then pointwise math + publish, then the deferred units inside the
+    // exchange latency of the value just published (SA has no mat-vec work: GRU1's input side is all precomputed).
+    const bool cond_live = t + 1 < S;
+    const int rows5 = p.rows5;
+    if (!warm && stage > 0) {
+        if (!gather_vec<PROF>(c, xb + (stage - 1) * VEC, epoch)) return false;   // H1 | H2 | Y1 | Y2
+        tick<PROF>(c, 3 * stage + (stage >= 3 ? 1 : 0));
+        run_critical(c, stage);
+        team_sync(c);
+        tick<PROF>(c, 3 * stage + 1 + (stage >= 3 ? 1 : 0));
+    }
+    if (!warm) {
         if (stage <= 1) {
-            if (role == 0) {
-                // GRU cell (torch gate order r, z, n): stage 0 = rnn1 (input side folded into P1),
-                // stage 1 = rnn2 (input side = Wih2x . h1 from the items + P2)
-                const int u = lane >> 3, f = lane & 7;
-                const float x = pg[PG_X + f];
-                const int P = stage == 0 ? PG_P1 : PG_P2, GH = stage == 0 ? PG_GH1 : PG_GH2, H = stage == 0 ? PG_H1 : PG_H2;
-                const int SU = stage == 0 ? SV_U1 : SV_U2, SB = stage == 0 ? SV_B1 : SV_B2;
-                float gi[3];
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    gi[q] = pg[P + q * 32 + lane] + x * sv[SU + q * 4 + u] + sv[SB + q * 4 + u];
-                    if (stage == 1) gi[q] += sum2(part, q, lane);
-                }
-                const float r = sigmoidf_(gi[0] + pg[GH + lane]);
-                const float z = sigmoidf_(gi[1] + pg[GH + 32 + lane]);
-                const float n = tanhf(gi[2] + r * pg[GH + 64 + lane]);
-                const float h = (1.0f - z) * n + z * pg[H + lane];
-                pg[H + lane] = h;
-                publish_line(xb + (stage == 0 ? XB_H1 : XB_H2), c.cta, lane, h, epoch);
-                tick<PROF>(c, stage == 0 ? 2 : 5);
-            } else if (role <= 3) {
-                const int q = role - 1;   // gh1 of the NEXT step: Whh1 . h1_t + b_hh1
-                pg[PG_GH1 + q * 32 + lane] = sum2(part, 3 + q, lane) + sv[SV_BHH1 + q * 4 + (lane >> 3)];
-            } else
-                pg[PG_F1 + lane] = sum2(part, 6, lane);                                    // Wfc1x . h1_t
+            if (tw == 0) gru_publish<PROF>(c, pg, xb, sv, part, stage, epoch);
+            if (stage == 0) return true;
         } else if (stage == 2) {
-            // S3: fc1 (h2 part + saved h1 part); gh2 of the next step
-            if (role == 0) {
+            if (tw == 0) {       // fc1: Wfc1x . (h1 + h2) with the h1 half saved by S2's deferred phase
                 const int u = lane >> 3, f = lane & 7;
-                float y = (sum2(part, 0, lane) + pg[PG_F1 + lane]) + pg[PG_P3 + lane] + pg[PG_X + f] * sv[SV_U3 + u] + sv[SV_B3 + u];
+                float y = (sum4(part, 0, lane) + pg[PG_F1 + lane]) + pg[PG_P3 + lane] + pg[PG_X + f] * sv[SV_U3 + u] + sv[SV_B3 + u];
                 y = fmaxf(y, 0.f);
                 publish_line(xb + XB_Y1, c.cta, lane, y, epoch);
                 tick<PROF>(c, 8);
-            } else {
-                const int q = role - 1;
-                pg[PG_GH2 + q * 32 + lane] = sum2(part, 1 + q, lane) + sv[SV_BHH2 + q * 4 + (lane >> 3)];
             }
         } else if (stage == 3) {
-            // S4: fc2; conditioning projections of step t+1
-            // conditioning units leave P1 r,z,n | P2 r,z,n | P3 | P4 in part slots 2..9
-            if (role == 0) {
-                if (!warm) {
-                    float y = sum2(part, 0, lane) + pg[PG_P4 + lane] + sv[SV_B4 + (lane >> 3)];
-                    y = fmaxf(y, 0.f);
-                    publish_line(xb + XB_Y2, c.cta, lane, y, epoch);
-                    tick<PROF>(c, 12);
-                }
-                if (t + 1 < S) pg[PG_P4 + lane] = part[9 * 32 + lane];
-            } else if (t + 1 < S) {
-                if (role <= 3) pg[PG_P1 + (role - 1) * 32 + lane] = part[(2 + (role - 1)) * 32 + lane];
-                else if (role <= 6) pg[PG_P2 + (role - 4) * 32 + lane] = part[(5 + (role - 4)) * 32 + lane];
-                else pg[PG_P3 + lane] = part[8 * 32 + lane];
+            if (tw == 0) {       // fc2
+                float y = sum4(part, 0, lane) + pg[PG_P4 + lane] + sv[SV_B4 + (lane >> 3)];
+                y = fmaxf(y, 0.f);
+                publish_line(xb + XB_Y2, c.cta, lane, y, epoch);
+                tick<PROF>(c, 12);
             }
         } else {
             // S5: logits of this CTA's rows5 classes, published fold-major
-            const float v = sum2(part, role, lane) + sv[SV_B5 + role * 4 + (lane >> 3)];
-            const int k = p.rows5 * c.cta + role * 4 + (lane >> 3);
-            st_pair(xb + XB_LG + (size_t)(lane & 7) * (p.rows5 * p.nprod5) + k, v, epoch);
+            for (int role = tw; role < (rows5 >> 2); role += nw) {
+                const float v = sum4(part, role, lane) + sv[SV_B5 + role * 4 + (lane >> 3)];
+                const int k = rows5 * c.cta + role * 4 + (lane >> 3);
+                st_pair(xb + XB_LG + (size_t)(lane & 7) * (rows5 * p.nprod5) + k, v, epoch);
+            }
             tick<PROF>(c, 15);
+            return true;
+        }
+    }
+    if (stage == 3) {
+        if (cond_live) cond_wait(c);                     // conditioning rows of step t+1 of this group
+        if (tw == nw - 1 && !warm) draws_issue(c, g, t); // draws consumed by the sample of step t (at SA of t+1)
+    }
+    if (stage != 3 || cond_live) run_deferred(c, stage);
+    team_sync(c);
+    tick<PROF>(c, 16 + (stage - 1));
+    if (stage == 3) {
+        // the staging buffer of this conditioning visit is free again: refill it for visit v + nbuf
+        if (tw == nw - 1) cond_issue_next(c);
+        if (++c.cv_buf == p.nbuf) {
+            c.cv_buf = 0;
+            c.cv_par ^= 1;
+        }
+    }
+    const int nroles = stage == 1 ? 4 : stage == 2 ? 3 : 8;
+#pragma unroll 1
+    for (int role = tw; role < nroles; role += nw) {
+        if (stage == 1) {
+            if (role < 3)        // gh1 of the NEXT step: Whh1 . h1_t + b_hh1
+                pg[PG_GH1 + role * 32 + lane] = sum2d(part, role, lane) + sv[SV_BHH1 + role * 4 + (lane >> 3)];
+            else                 // Wfc1x . h1_t, consumed by S3 of this step
+                pg[PG_F1 + lane] = sum2d(part, 3, lane);
+        } else if (stage == 2) {
+            pg[PG_GH2 + role * 32 + lane] = sum2d(part, role, lane) + sv[SV_BHH2 + role * 4 + (lane >> 3)];
+        } else if (cond_live) {
+            // conditioning projections of step t+1: units 0-2 P1 | 3-5 P2 | 6 P3 | 7 P4
+            const int dst = role < 3 ? PG_P1 + role * 32 : role < 6 ? PG_P2 + (role - 3) * 32 : role == 6 ? PG_P3 : PG_P4;
+            pg[dst + lane] = part[(DEF0 + role) * 32 + lane];
         }
     }
     if (stage == 3 && tw == nw - 1 && !warm) draws_commit(c, g);

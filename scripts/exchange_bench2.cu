@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(NT, 1) exch(int mode, int iters, int lines, in
     if (mode == 0) {
         for (int it = 0; it < iters; ++it) {
             const unsigned epoch = it + 1;
-            unsigned long long *lb = ll + (size_t)(it % 5) * 4096;
-            if (warp == 0) st_pair(lb + cta * 32 + lane, (float)(it + cta), epoch);
+            unsigned long long *lb = ll + (size_t)((R & 2) ? (it & 3) : (it % 5)) * 4096;
+            if (warp == 0) st_pair(lb + cta * 32 + lane, (R & 1) ? acc + (float)it : (float)(it + cta), epoch);
             uint4 v[4];
             for (int j = 0; j < 4; ++j) v[j] = ld_volatile4(lb + 2 * (tid + j * NT));
             for (int spin = 0;; ++spin) {
@@ -321,12 +321,14 @@ int main()
     CK(cudaMalloc(&buf, bufbytes)); CK(cudaMalloc(&ll, 5 * 4096 * 8)); CK(cudaMalloc(&errors, 4)); CK(cudaMalloc(&sink, 16));
     CK(cudaMalloc(&cycles, 148 * 16 * 8));
     const int smem = 96 * 1024;
-    CK(cudaFuncSetAttribute(exch, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaFuncSetAttribute(exch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(math, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     struct Case { int mode, lines, R; const char *name; };
     const Case cases[] = {
-        {0, 256, 1, "LL pairs 32 KiB, 512 thr"},
+        {0, 256, 0, "LL pairs 32 KiB, 512 thr"},
+        {0, 256, 1, "LL pairs 32 KiB, dependent publish value"},
+        {0, 256, 3, "LL pairs 32 KiB, dependent value + 4 slots"},
         {1, 128, 1, "poison 16 KiB, 512 thr, R=1"},
         {1, 128, 2, "poison 16 KiB, 512 thr, R=2"},
         {1, 128, 4, "poison 16 KiB, 512 thr, R=4"},
@@ -337,7 +339,11 @@ int main()
         {2, 128, 1, "poison 16 KiB, 3 teams x 160 thr (per round of 3 exchanges)"},
         {2, 128, 2, "poison 16 KiB, 3 teams x 160 thr, R=2"},
     };
+    for (int big = 0; big < 2; ++big)
     for (const Case &c : cases) {
+        if (big && c.mode != 0) continue;
+        const int smem = big ? 200 * 1024 : 96 * 1024;
+        if (big) printf("(dynamic smem 200 KiB) ");
         int iters = 2000;
         float ms = 0;
         int herr = 0;
