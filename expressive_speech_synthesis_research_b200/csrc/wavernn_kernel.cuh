@@ -370,10 +370,11 @@ __device__ __forceinline__ void wait_ready(Ctx &c, const unsigned long long *fir
 // Team-uniform result: false = the watchdog fired somewhere in this team (the kernel then exits and the
 // host reports WRNN_ERR_TIMEOUT).
 template <bool PROF>
-__device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src, unsigned epoch)
+__device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src, unsigned epoch, int prof_slot = 19)
 {
     float *dst = c.stage;
     constexpr int NCH = VEC / 2;
+    tick<PROF>(c, 0);                            // everything between the previous phase and the first poll
     if (c.p->poll_mode == 1) wait_ready(c, src + 31, 32, NCTA, epoch);
     if (c.p->poll_mode == 2) team_sync(c);       // nobody polls before this CTA has published its own line
 #pragma unroll 1
@@ -408,9 +409,8 @@ __device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src
             *reinterpret_cast<float2 *>(dst + k * BT + (f0 ^ (k & 2))) = (k & 1) ? make_float2(b, a) : make_float2(a, b);
         }
     }
-    tick<PROF>(c, 19);                           // own chunks validated + scattered
+    tick<PROF>(c, prof_slot);                    // own chunks validated + scattered
     team_sync(c);
-    tick<PROF>(c, 20);                           // waiting for the other warps at the barrier
     return *c.abort_flag == 0;
 }
 
@@ -784,6 +784,9 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     const float *sv = small(c);
     const float *part = c.part;
     const bool warm = t < 0;
+    // The refill of a conditioning staging buffer costs its issuing warp ~1400 cycles; unless the very next visit
+    // of this team needs the buffer (one buffer, several groups) it is postponed to the deferred phase of S2.
+    const bool late_issue = p.nbuf == 2 || c.ng == 1;
 
     if (warm) team_sync(c);                              // no gather barrier in the warm-up pass: part is reused
     if (stage == 0) {
@@ -818,7 +821,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     const bool cond_live = t + 1 < S;
     const int rows5 = p.rows5;
     if (!warm && stage > 0) {
-        if (!gather_vec<PROF>(c, xb + (stage - 1) * VEC, epoch)) return false;   // H1 | H2 | Y1 | Y2
+        if (!gather_vec<PROF>(c, xb + (stage - 1) * VEC, epoch, 19 + stage)) return false;   // H1 | H2 | Y1 | Y2
         tick<PROF>(c, 3 * stage + (stage >= 3 ? 1 : 0));
         run_critical(c, stage);
         team_sync(c);
@@ -854,6 +857,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
             return true;
         }
     }
+    if (stage == 1 && late_issue && tw == nw - 1) cond_issue_next(c);
     if (stage == 3) {
         if (cond_live) cond_wait(c);                     // conditioning rows of step t+1 of this group
         if (tw == nw - 1 && !warm) draws_issue(c, g, t); // draws consumed by the sample of step t (at SA of t+1)
@@ -863,7 +867,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     tick<PROF>(c, 16 + (stage - 1));
     if (stage == 3) {
         // the staging buffer of this conditioning visit is free again: refill it for visit v + nbuf
-        if (tw == nw - 1) cond_issue_next(c);
+        if (tw == nw - 1 && !late_issue) cond_issue_next(c);
         if (++c.cv_buf == p.nbuf) {
             c.cv_buf = 0;
             c.cv_par ^= 1;

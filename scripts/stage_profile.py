@@ -10,10 +10,10 @@ sys.path.insert(0, ROOT)
 from expressive_speech_synthesis_research_b200 import WaveRNN  # noqa: E402
 from oracle import synth  # noqa: E402
 
-SLOTS = ["(unused)", "SA poll+sample", "SA gru1+publish", "S2 gather(h1)", "S2 items", "S2 finalize",
-         "S3 gather(h2)", "S3 items", "S3 finalize", "S4 cond_visit", "S4 gather(y1)", "S4 items", "S4 finalize",
+SLOTS = ["before first poll: roles + loop + visit entry (4 gathers)", "SA poll+sample", "SA gru1+publish", "S2 gather(h1)", "S2 items", "S2 finalize",
+         "S3 gather(h2)", "S3 items", "S3 finalize", "gather: poll rounds (count, 4 gathers)", "S4 gather(y1)", "S4 items", "S4 finalize",
          "S5 gather(y2)", "S5 items", "S5 finalize", "S2 deferred+barrier", "S3 deferred+barrier",
-         "S4 deferred(cond)+barrier", "gather: own chunks", "gather: barrier wait"]
+         "S4 deferred(cond)+barrier", "(unused)", "S2 wait own chunks (H1)", "S3 wait own chunks (H2)", "S4 wait own chunks (Y1)", "S5 wait own chunks (Y2)"]
 
 
 def main():
@@ -26,7 +26,9 @@ def main():
     S = 3000
     cases = [(8, None, 0), (14, None, 0), (20, None, 0), (64, None, 0)]
     for B, force, stagger in cases:
-        os.environ["WRNN_POLL_MODE"] = str(-stagger) if stagger < 0 else "0"
+        os.environ["WRNN_POLL_MODE"] = str(-stagger) if -10 < stagger < 0 else "0"
+        os.environ["WRNN_DEBUG"] = str(-stagger - 100) if -1000 < stagger <= -100 else "0"
+        os.environ["WRNN_XB_SHIFT"] = str(-stagger - 1000) if stagger <= -1000 else "0"
         os.environ["WRNN_STAGGER_CYCLES"] = str(max(stagger, 0))
         if force is None:
             os.environ.pop("WRNN_FORCE_TEAMS", None)
@@ -44,7 +46,7 @@ def main():
             print("B=%d G=%d teams<=%s stagger=%d profiling=%s: %.3f ms, %.2f us/step" % (B, (B + 7) // 8, force or "3", stagger, prof, ms, ms * 1e3 / S), flush=True)
         cyc = eng.stage_cycles().astype(np.float64) / S
         G = (B + 7) // 8
-        tot = cyc[:, :21].sum(1)
+        tot = cyc[:, :24].sum(1)
         print("  cycles/step (all groups): cta0 total %.0f  mean %.0f  max %.0f  => %.2f GHz effective" % (
             tot[0], tot.mean(), tot.max(), tot.mean() / (ms * 1e3 / S) / 1e3))
         for i, name in enumerate(SLOTS):
