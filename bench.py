@@ -264,6 +264,7 @@ def run_b200(args):
             t_sync = None
         us_per_step = k_ms * 1e3 / wl["S"]
         groups = (wl["folds"] + 7) // 8
+        teams = min(groups, 3)
         fp32_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12
         lat_floor = 5 * t_sync if t_sync else None
         fma_floor = wl["folds"] * FLOP_PER_FOLD_STEP[args.mode] / (fp32_peak * 1e12) * 1e6
@@ -281,9 +282,10 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "kernel": "wavernn_persistent_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
                          "kernel_ms_per_launch": k_ms,
-                         "note": "HBM is not what bounds this kernel (840 B per fold-step); the binding terms are the "
-                                 "step-latency model below (SURVEY.md 8d)"},
-            "step_latency_model": {"us_per_step": us_per_step, "exchanges_per_step": 5, "groups": groups,
+                         "note": "HBM is not what bounds this kernel (840 B per fold-step, measured dram traffic ~0.7 GB/s); "
+                                 "the binding terms are the step-latency model below (SURVEY.md 8d, DESIGN.md 7): five "
+                                 "dependent grid-level exchanges per step plus the FFMA2 / shared-memory floors"},
+            "step_latency_model": {"us_per_step": us_per_step, "exchanges_per_step": 5, "groups": groups, "teams_per_cta": teams,
                                    "t_exchange_us_measured": t_sync, "latency_floor_us": lat_floor,
                                    "fp32_fma_floor_us": fma_floor, "fp32_peak_tflops_at_clock": fp32_peak,
                                    "frac_of_floor": (max(lat_floor or 0.0, fma_floor) / us_per_step) if us_per_step else None,
