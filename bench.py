@@ -203,6 +203,7 @@ def run_b200(args):
 
     def device_step(seed):
         # inputs already resident in HBM; conditioning net + step loop + epilogue, no host copies
+        model.eval()                      # generate() leaves the module in train() like the reference (:241)
         with torch.no_grad():
             return model._generate_on_device(eng, dev, mel_dev, True, TARGET, OVERLAP, True, None, seed, None, False)[0]
 
