@@ -74,7 +74,7 @@ __host__ __device__ inline SmemMap smem_map(int rows5, int mode, int C, int T, i
     m.priv = m.w + w_total(rows5);
     m.fs = m.priv + MAXG * PG_SIZE;                 // [MAXG*8] fold starts | [MAXG*8] fold limits (long long)
     m.prof = m.fs + 4 * MAXG * BT;
-    m.team0 = m.prof + 64;
+    m.team0 = m.prof + 2 * 32;
     m.stage_floats = stage_floats_for(mode, C);
     m.nbuf = nbuf;
     m.t_stage = 0;
@@ -106,7 +106,7 @@ struct KParams {
     int probe_iters;
     long long *prof;                   // optional [NCTA][PROF_SLOTS] per-stage cycle counters (clock64, team 0 thread 0)
 };
-constexpr int PROF_SLOTS = 24;
+constexpr int PROF_SLOTS = 32;
 // exchange buffer of one group, in pairs: H1 | H2 | Y1 | Y2 as [k][8 folds], logits as [8 folds][cpad]
 constexpr int XB_H1 = 0, XB_H2 = VEC, XB_Y1 = 2 * VEC, XB_Y2 = 3 * VEC, XB_LG = 4 * VEC;
 __host__ __device__ constexpr int xb_group(int cpad) { return 4 * VEC + cpad * BT; }
@@ -374,7 +374,7 @@ __device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src
 {
     float *dst = c.stage;
     constexpr int NCH = VEC / 2;
-    tick<PROF>(c, 0);                            // everything between the previous phase and the first poll
+    tick<PROF>(c, prof_slot + 4);                // everything between the previous phase and the first poll
     if (c.p->poll_mode == 1) wait_ready(c, src + 31, 32, NCTA, epoch);
     if (c.p->poll_mode == 2) team_sync(c);       // nobody polls before this CTA has published its own line
 #pragma unroll 1
@@ -948,7 +948,7 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
             *reinterpret_cast<int *>(tb + c.m.t_ctl + 8) = 0;
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
-        if (c.tid < 64) sm[c.m.prof + c.tid] = 0.f;
+        if (c.tid < 2 * PROF_SLOTS) sm[c.m.prof + c.tid] = 0.f;
         __syncthreads();
         const float *sv = small(c);
         for (int g = 0; g < G; ++g) {           // h = 0  =>  gh = b_hh  (fatchord_version.py:173-174)

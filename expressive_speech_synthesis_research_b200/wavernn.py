@@ -119,11 +119,11 @@ class _Engine:
 
     def stage_cycles(self, enable=None):
         """enable=True/False toggles in-kernel stage timing; None returns the last launch's counters
-        as an int64 array [128, 24]."""
+        as an int64 array [128, 32]."""
         if enable is not None:
             _lib.check(self.lib.wrnn_set_profiling(self.handle, int(bool(enable))))
             return None
-        out = np.zeros((128, 24), dtype=np.int64)
+        out = np.zeros((128, 32), dtype=np.int64)
         _lib.check(self.lib.wrnn_get_stage_cycles(self.handle, out.ctypes.data, out.size))
         return out
 

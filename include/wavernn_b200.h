@@ -159,7 +159,7 @@ int32_t wrnn_get_info(wrnn_handle *h, wrnn_info *out);
 
 /* Optional in-kernel stage timing (development / profiles/): when enabled, thread 0 of every
  * CTA accumulates clock64() cycles per (stage, phase) of the step loop; the counters of the
- * last wrnn_generate_folds launch are returned as int64 [128 CTAs][24 slots]
+ * last wrnn_generate_folds launch are returned as int64 [128 CTAs][32 slots]
  * (slot map in csrc/wavernn_kernel.cuh).  Adds ~20 clock reads per step. */
 int32_t wrnn_set_profiling(wrnn_handle *h, int32_t enable);
 int32_t wrnn_get_stage_cycles(wrnn_handle *h, int64_t *out /* [host] */, int32_t n);
