@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--geometry", default="fatchord", choices=list(GEOMETRY))
     ap.add_argument("--mode", default="RAW", choices=["RAW", "MOL"])
     ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
+                    help="resident weight precision of the CUDA path (bf16 = BASELINE.json configs[2] comparison; the headline is fp32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-sample-steps", type=int, default=1200)
     return ap.parse_args()
@@ -197,6 +199,7 @@ def run_b200(args):
     wl = workload(args)
     torch.manual_seed(0)
     model = WaveRNN(**model_kwargs(args.mode, args.geometry)).to(dev)
+    model.precision = args.precision
     mel_host = torch.rand(1, 80, wl["T"], generator=torch.Generator().manual_seed(rank)).pin_memory()
     mel_dev = mel_host.to(dev)
     eng = model._engine(dev)
@@ -272,7 +275,8 @@ def run_b200(args):
         line = {
             "metric": "generated_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": n,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "f32 math, bf16 resident weights", "data": "synthetic",
             "rtf": (t_dev / args.steps) / (wl["wave_len"] / wl["sr"]),
             "config": config_dict(args, wl, n),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(mel_host.numel() * 4),

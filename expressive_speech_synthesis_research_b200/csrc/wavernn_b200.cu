@@ -38,6 +38,7 @@ struct wrnn_handle {
     int rows5 = 4, nprod5 = 128, cpad = 512, n_u = 1;
     int smem_bytes = 0, smem_limit = 0;   // dynamic shared memory of the last launch / opt-in limit of the device
     int last_teams = 1;
+    int bf16w = 0;                        // precision bf16: item images hold bf16 weights
     bool loaded = false;
     float *wimg = nullptr;
     unsigned long long *xb = nullptr;   // LL exchange buffers
@@ -82,8 +83,8 @@ static int32_t derive_layout(const wrnn_config &c, int &rows5, int &nprod5, int 
         return fail(WRNN_ERR_INVALID, "this build keeps rnn_dims == fc_dims == %d resident (got %d / %d)", HID, c.rnn_dims, c.fc_dims);
     if (c.feat_dims != 80 || c.aux_dims != 32)
         return fail(WRNN_ERR_INVALID, "conditioning layout is fixed to feat_dims 80 + 4 x aux_dims 32 (got %d, %d)", c.feat_dims, c.aux_dims);
-    if (c.precision != WRNN_PREC_FP32)
-        return fail(WRNN_ERR_INVALID, "precision %d not available in this build (fp32 only)", c.precision);
+    if (c.precision != WRNN_PREC_FP32 && c.precision != WRNN_PREC_BF16)
+        return fail(WRNN_ERR_INVALID, "unknown precision %d", c.precision);
     if (c.mode == WRNN_MODE_RAW) {
         const int C = c.n_classes;
         if (C != 64 && C != 128 && C != 256 && C != 512 && C != 1024)
@@ -128,7 +129,8 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
     h->n_u = n_u;
     h->cpad = rows5 * nprod5;
     h->smem_limit = (int)prop.sharedMemPerBlockOptin;
-    h->smem_bytes = smem_map(rows5, cfg->mode, cfg->n_classes, 1, 1).total * (int)sizeof(float);   // smallest configuration
+    h->bf16w = cfg->precision == WRNN_PREC_BF16 ? 1 : 0;
+    h->smem_bytes = smem_map(rows5, cfg->mode, cfg->n_classes, 1, 1, h->bf16w).total * (int)sizeof(float);   // smallest configuration
     if (h->smem_bytes > h->smem_limit) {
         const int need = h->smem_bytes;
         delete h;
@@ -141,6 +143,7 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
         return fail(WRNN_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e));          \
     }
     H_TRY(cudaFuncSetAttribute(wavernn_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_limit));
+    H_TRY(cudaFuncSetAttribute(wavernn_persistent_kernel_bf16w, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_limit));
     H_TRY(cudaFuncSetAttribute(wavernn_exchange_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_limit));
     H_TRY(cudaFuncSetAttribute(wavernn_persistent_kernel_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_limit));
     int occ = 0;
@@ -149,7 +152,7 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
         wrnn_destroy(h);
         return fail(WRNN_ERR_CUDA, "persistent kernel does not fit on an SM");
     }
-    H_TRY(cudaMalloc(&h->wimg, (size_t)NCTA * w_total(rows5) * sizeof(float)));
+    H_TRY(cudaMalloc(&h->wimg, (size_t)NCTA * w_image_floats(rows5, h->bf16w) * sizeof(float)));
     H_TRY(cudaMalloc(&h->xb, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long) + (1 << 20)));
     H_TRY(cudaMalloc(&h->status, 4 * sizeof(int)));
     H_TRY(cudaEventCreate(&h->ev0));
@@ -297,11 +300,38 @@ static void pack_images(int C, int rows5, const wrnn_weights *w, std::vector<flo
     }
 }
 
+// fp32 -> bf16, round to nearest even (finite inputs)
+static unsigned short bf16_rne(float f)
+{
+    unsigned u;
+    memcpy(&u, &f, 4);
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (unsigned short)(u >> 16);
+}
+
+// Per-CTA images in the layout the kernel keeps resident.  bf16 precision: every item image is rounded to bf16
+// (after the fp64 folding) and packed two per float slot; the small vectors stay fp32.
+static void finish_images(int rows5, int bf16w, const std::vector<float> &img32, std::vector<float> &out)
+{
+    if (!bf16w) {
+        out = img32;
+        return;
+    }
+    const size_t per32 = (size_t)w_total(rows5), per = (size_t)w_image_floats(rows5, 1), items = (size_t)w_small(rows5);
+    out.assign((size_t)NCTA * per, 0.f);
+    for (int c = 0; c < NCTA; ++c) {
+        const float *src = &img32[(size_t)c * per32];
+        unsigned short *dst = reinterpret_cast<unsigned short *>(&out[(size_t)c * per]);
+        for (size_t i = 0; i < items; ++i) dst[i] = bf16_rne(src[i]);
+        memcpy(&out[(size_t)c * per + items / 2], src + items, SV_SIZE * sizeof(float));
+    }
+}
+
 extern "C" int64_t wrnn_packed_floats(const wrnn_config *cfg)
 {
     int rows5, nprod5, n_u;
     if (!cfg || derive_layout(*cfg, rows5, nprod5, n_u)) return -1;
-    return (int64_t)NCTA * w_total(rows5);
+    return (int64_t)NCTA * w_image_floats(rows5, cfg->precision == WRNN_PREC_BF16 ? 1 : 0);
 }
 
 extern "C" int32_t wrnn_pack_weights_host(const wrnn_config *cfg, const wrnn_weights *w, float *out, int64_t out_floats)
@@ -310,9 +340,12 @@ extern "C" int32_t wrnn_pack_weights_host(const wrnn_config *cfg, const wrnn_wei
     int rows5, nprod5, n_u;
     int32_t rc = derive_layout(*cfg, rows5, nprod5, n_u);
     if (rc) return rc;
-    if (out_floats != (int64_t)NCTA * w_total(rows5)) return fail(WRNN_ERR_INVALID, "out_floats must be %lld", (long long)NCTA * w_total(rows5));
-    std::vector<float> img;
-    pack_images(cfg->n_classes, rows5, w, img);
+    const int bf16w = cfg->precision == WRNN_PREC_BF16 ? 1 : 0;
+    const long long want = (long long)NCTA * w_image_floats(rows5, bf16w);
+    if (out_floats != want) return fail(WRNN_ERR_INVALID, "out_floats must be %lld", want);
+    std::vector<float> img32, img;
+    pack_images(cfg->n_classes, rows5, w, img32);
+    finish_images(rows5, bf16w, img32, img);
     memcpy(out, img.data(), img.size() * sizeof(float));
     return WRNN_OK;
 }
@@ -324,8 +357,9 @@ extern "C" int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w)
     for (int i = 0; i < 16; ++i)
         if (!pp[i]) return fail(WRNN_ERR_INVALID, "weight pointer %d is null", i);
     CUDA_TRY(cudaSetDevice(h->device));
-    std::vector<float> img;
-    pack_images(h->cfg.n_classes, h->rows5, w, img);
+    std::vector<float> img32, img;
+    pack_images(h->cfg.n_classes, h->rows5, w, img32);
+    finish_images(h->rows5, h->bf16w, img32, img);
     CUDA_TRY(cudaMemcpy(h->wimg, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
     h->loaded = true;
     return WRNN_OK;
@@ -338,7 +372,7 @@ static void choose_teams(const wrnn_handle *h, int G, int &T, int &nbuf)
 {
     for (T = G < MAXT ? G : MAXT; T >= 1; --T)
         for (nbuf = 2; nbuf >= 1; --nbuf)
-            if (smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, T, nbuf).total * (int)sizeof(float) <= h->smem_limit) return;
+            if (smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, T, nbuf, h->bf16w).total * (int)sizeof(float) <= h->smem_limit) return;
     T = 1;
     nbuf = 1;
 }
@@ -355,7 +389,7 @@ static int32_t launch_chunk(wrnn_handle *h, KParams &p, cudaStream_t st, bool pr
         if (force && atoi(force) >= 1 && atoi(force) < p.T) {
             p.T = atoi(force);
             p.nbuf = 2;
-            if (smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, p.T, 2).total * (int)sizeof(float) > h->smem_limit) p.nbuf = 1;
+            if (smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, p.T, 2, h->bf16w).total * (int)sizeof(float) > h->smem_limit) p.nbuf = 1;
         }
     }
     {
@@ -364,13 +398,14 @@ static int32_t launch_chunk(wrnn_handle *h, KParams &p, cudaStream_t st, bool pr
         const char *pm = getenv("WRNN_POLL_MODE");
         p.poll_mode = pm ? atoi(pm) : 0;
     }
-    h->smem_bytes = smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, p.T, p.nbuf).total * (int)sizeof(float);
+    h->smem_bytes = smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, p.T, p.nbuf, h->bf16w).total * (int)sizeof(float);
     h->last_teams = p.T;
     // epochs restart at 1 every launch: clear stale {value, epoch} pairs of the previous one
     CUDA_TRY(cudaMemsetAsync(h->xb, 0, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long) + (1 << 20), st));
     CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     const void *fn = probe ? (const void *)wavernn_exchange_probe_kernel
+                           : h->bf16w ? (const void *)wavernn_persistent_kernel_bf16w
                            : (p.prof ? (const void *)wavernn_persistent_kernel_prof : (const void *)wavernn_persistent_kernel);
     CUDA_TRY(cudaLaunchCooperativeKernel(fn,
                                          dim3(NCTA), dim3(NTHREADS), args, (size_t)h->smem_bytes, st));
@@ -401,6 +436,7 @@ static void fill_common(wrnn_handle *h, KParams &p)
     p.rows5 = h->rows5;
     p.nprod5 = h->nprod5;
     p.n_u = h->n_u;
+    p.bf16w = h->bf16w;
     p.feat = h->cfg.feat_dims;
     p.auxw = 4 * h->cfg.aux_dims;
 }

@@ -54,6 +54,9 @@ __host__ __device__ constexpr int w_small(int rows5) { return w_mc(rows5) + COND
 constexpr int SV_U1 = 0, SV_B1 = 12, SV_BHH1 = 24, SV_U2 = 36, SV_B2 = 48, SV_BHH2 = 60,
               SV_U3 = 72, SV_B3 = 76, SV_B4 = 80, SV_B5 = 84, SV_SIZE = 128;
 __host__ __device__ constexpr int w_total(int rows5) { return w_small(rows5) + SV_SIZE; }
+// bf16-weight images (WRNN_PREC_BF16): every item image holds bf16 instead of fp32, i.e. all item offsets halve
+// (they are multiples of ITEM); the small vectors stay fp32.  The arithmetic stays fp32 FFMA2.
+__host__ __device__ constexpr int w_image_floats(int rows5, int bf16w) { return (bf16w ? w_small(rows5) / 2 : w_small(rows5)) + SV_SIZE; }
 
 // ---- per-group private state (floats) -----------------------------------------------------
 constexpr int PG_GH1 = 0, PG_GH2 = 96, PG_P1 = 192, PG_P2 = 288, PG_P3 = 384, PG_P4 = 416,
@@ -67,11 +70,11 @@ struct SmemMap {
     int t_stage, t_part, t_cst, t_ctl;      // offsets inside a team block
 };
 __host__ __device__ inline int stage_floats_for(int mode, int C) { return (mode == 0 && BT * C > VEC) ? BT * C : VEC; }
-__host__ __device__ inline SmemMap smem_map(int rows5, int mode, int C, int T, int nbuf)
+__host__ __device__ inline SmemMap smem_map(int rows5, int mode, int C, int T, int nbuf, int bf16w = 0)
 {
     SmemMap m;
     m.w = 0;
-    m.priv = m.w + w_total(rows5);
+    m.priv = m.w + w_image_floats(rows5, bf16w);
     m.fs = m.priv + MAXG * PG_SIZE;                 // [MAXG*8] fold starts | [MAXG*8] fold limits (long long)
     m.prof = m.fs + 4 * MAXG * BT;
     m.team0 = m.prof + 2 * 32;
@@ -100,6 +103,7 @@ struct KParams {
     int B, S, G, C, mode, rows5, nprod5, n_u;   // n_u: uniforms per fold-step (1 RAW, 11 MOL)
     int feat, auxw;                    // 80, 128
     int T, nbuf;                       // teams per CTA, conditioning staging buffers per team
+    int bf16w;                         // 1: item images hold bf16 weights (precision bf16), else fp32
     int stagger;                       // start-up delay per team index (cycles): breaks the lockstep of the teams
     int poll_mode;                     // 1: one warp per team polls a sentinel pair per producer, the others wait at a barrier
     int group_fold0[MAXG], group_nf[MAXG];
@@ -195,14 +199,25 @@ __device__ __forceinline__ f32x2 pack2(float lo, float hi)
 __device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ void fma2(f32x2 &d, f32x2 a, f32x2 b) { asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b)); }
 
+// The four k-consecutive weights (k = kbase + lane + 32 i) of row slot r of an item image: one LDS.128 of fp32, or one
+// LDS.64 of bf16 widened to fp32 (exact) when the image holds bf16 weights.
+template <bool BF16W>
+__device__ __forceinline__ float4 ld_w4(const float *wimg, int r, int lane)
+{
+    if (!BF16W) return *reinterpret_cast<const float4 *>(wimg + (r * 32 + lane) * 4);
+    const uint2 u = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned short *>(wimg) + (r * 32 + lane) * 4);
+    return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+
 // One work item: acc[slot r][fold slots] += W[4][128 k] * X[128 k][8 folds] for this lane's four k.
 // wimg: item image (see above).  xs: exchanged vector in shared memory at row kbase (a multiple of 128).
 // acc[r][j] holds fold slots (2j, 2j+1) of row slot r.
+template <bool BF16W>
 __device__ __forceinline__ void item_fma(const float *wimg, const float *xs, int lane, f32x2 (&acc)[4][4])
 {
     float4 w[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const float4 *>(wimg + (r * 32 + lane) * 4);
+    for (int r = 0; r < 4; ++r) w[r] = ld_w4<BF16W>(wimg, r, lane);
     const int sw = ((lane >> 2) & 1) * 4;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -223,11 +238,12 @@ __device__ __forceinline__ void item_fma(const float *wimg, const float *xs, int
 }
 // The same item against the fold-major conditioning staging buffer cst[fold][208] (k = kbase + lane + 32 i;
 // k >= 208 is the zero padding of the 256-wide conditioning K space).
+template <bool BF16W>
 __device__ __forceinline__ void item_fma_cond(const float *wimg, const float *cst, int kbase, int lane, f32x2 (&acc)[4][4])
 {
     float4 w[4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const float4 *>(wimg + (r * 32 + lane) * 4);
+    for (int r = 0; r < 4; ++r) w[r] = ld_w4<BF16W>(wimg, r, lane);
     const int fx = lane & 7;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -331,7 +347,7 @@ __device__ __forceinline__ void tick(Ctx &c, int slot)
 }
 
 __device__ __forceinline__ float *priv(const Ctx &c, int g) { return c.sm + c.m.priv + g * PG_SIZE; }
-__device__ __forceinline__ const float *small(const Ctx &c) { return c.sm + c.m.w + w_small(c.p->rows5); }
+__device__ __forceinline__ const float *small(const Ctx &c) { return c.sm + c.m.w + (w_image_floats(c.p->rows5, c.p->bf16w) - SV_SIZE); }
 __device__ __forceinline__ unsigned long long *xb_base(const Ctx &c, int g)
 {
     return c.p->xb + (size_t)g * xb_group(c.p->rows5 * c.p->nprod5);
@@ -692,23 +708,27 @@ __device__ __forceinline__ void zero_acc(f32x2 (&acc)[4][4])
         for (int j = 0; j < 4; ++j) acc[r][j] = 0ull;
 }
 
+template <bool BF16W>
 __device__ __forceinline__ void run_critical(Ctx &c, int stage)
 {
+    constexpr int SH = BF16W ? 1 : 0;            // item offsets halve when the images hold bf16
     const int rows5 = c.p->rows5;
     const int n = stage == 1 ? 12 : stage == 4 ? rows5 : 4;
     const int woff = stage == 1 ? W_M2 : stage == 2 ? W_M3 : stage == 3 ? W_M4 : W_M5;
-    const float *W = c.sm + c.m.w + woff;
+    const float *W = c.sm + c.m.w + (woff >> SH);
 #pragma unroll 1
     for (int i = c.tw; i < n; i += c.nw) {
         f32x2 acc[4][4];
         zero_acc(acc);
-        item_fma(W + i * ITEM, c.stage + (i & 3) * 128 * BT, c.lane, acc);
+        item_fma<BF16W>(W + ((i * ITEM) >> SH), c.stage + (i & 3) * 128 * BT, c.lane, acc);
         c.part[i * 32 + c.lane] = reduce_scatter32(acc);
     }
 }
 
+template <bool BF16W>
 __device__ __forceinline__ void run_deferred(Ctx &c, int stage)
 {
+    constexpr int SH = BF16W ? 1 : 0;
     const int rows5 = c.p->rows5;
     const int n = stage == 1 ? 8 : stage == 2 ? 6 : 8;
     const float *W = c.sm + c.m.w;
@@ -725,14 +745,14 @@ __device__ __forceinline__ void run_deferred(Ctx &c, int stage)
             const int chunk0 = u == 7 ? 1 : 0;
             const float *cst = c.cst + c.cv_buf * (BT * CROW);
 #pragma unroll 1
-            for (int q = 0; q < nit; ++q) item_fma_cond(W + w_mc(rows5) + (it0 + q) * ITEM, cst, (chunk0 + q) * 128, c.lane, acc);
+            for (int q = 0; q < nit; ++q) item_fma_cond<BF16W>(W + ((w_mc(rows5) + (it0 + q) * ITEM) >> SH), cst, (chunk0 + q) * 128, c.lane, acc);
         } else {
             const int rg = u >> 1, h = u & 1;
             // S2: row groups 3..5 of M2 (Whh1), then Wfc1x = row group 0 of M3;  S3: row groups 1..3 of M3 (Whh2)
             const int woff = stage == 1 ? (rg < 3 ? W_M2 + ((3 + rg) * 4 + 2 * h) * ITEM : W_M3 + 2 * h * ITEM)
                                         : W_M3 + ((1 + rg) * 4 + 2 * h) * ITEM;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) item_fma(W + woff + q * ITEM, c.stage + (2 * h + q) * 128 * BT, c.lane, acc);
+            for (int q = 0; q < 2; ++q) item_fma<BF16W>(W + ((woff + q * ITEM) >> SH), c.stage + (2 * h + q) * 128 * BT, c.lane, acc);
         }
         c.part[(DEF0 + u) * 32 + c.lane] = reduce_scatter32(acc);
     }
@@ -773,7 +793,7 @@ __device__ __forceinline__ void gru_publish(Ctx &c, float *pg, unsigned long lon
 }
 
 // One visit: stage `stage` of step t for group g.  Returns false when the watchdog fired (team-uniform).
-template <bool PROF>
+template <bool PROF, bool BF16W>
 __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
 {
     const KParams &p = *c.p;
@@ -823,7 +843,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     if (!warm && stage > 0) {
         if (!gather_vec<PROF>(c, xb + (stage - 1) * VEC, epoch, 19 + stage)) return false;   // H1 | H2 | Y1 | Y2
         tick<PROF>(c, 3 * stage + (stage >= 3 ? 1 : 0));
-        run_critical(c, stage);
+        run_critical<BF16W>(c, stage);
         team_sync(c);
         tick<PROF>(c, 3 * stage + 1 + (stage >= 3 ? 1 : 0));
     }
@@ -862,7 +882,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
         if (cond_live) cond_wait(c);                     // conditioning rows of step t+1 of this group
         if (tw == nw - 1 && !warm) draws_issue(c, g, t); // draws consumed by the sample of step t (at SA of t+1)
     }
-    if (stage != 3 || cond_live) run_deferred(c, stage);
+    if (stage != 3 || cond_live) run_deferred<BF16W>(c, stage);
     team_sync(c);
     tick<PROF>(c, 16 + (stage - 1));
     if (stage == 3) {
@@ -893,7 +913,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     return true;
 }
 
-template <bool PROF>
+template <bool PROF, bool BF16W>
 __device__ __forceinline__ void persistent_body(const KParams &prm)
 {
     extern __shared__ __align__(128) float sm[];
@@ -901,7 +921,7 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
     Ctx c;
     c.p = &prm;
     c.sm = sm;
-    c.m = smem_map(p.rows5, p.mode, p.C, p.T, p.nbuf);
+    c.m = smem_map(p.rows5, p.mode, p.C, p.T, p.nbuf, BF16W ? 1 : 0);
     c.tid = threadIdx.x;
     c.lane = c.tid & 31;
     c.warp = c.tid >> 5;
@@ -929,9 +949,10 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
 
     // ---- prologue (whole CTA): resident weights, zero state ------------------------------------
     {
-        const float4 *src = reinterpret_cast<const float4 *>(p.wimg + (size_t)c.cta * w_total(p.rows5));
+        const int wfloats = w_image_floats(p.rows5, BF16W ? 1 : 0);
+        const float4 *src = reinterpret_cast<const float4 *>(p.wimg + (size_t)c.cta * wfloats);
         float4 *dst = reinterpret_cast<float4 *>(sm + c.m.w);
-        for (int i = c.tid; i < w_total(p.rows5) / 4; i += NTHREADS) dst[i] = src[i];
+        for (int i = c.tid; i < wfloats / 4; i += NTHREADS) dst[i] = src[i];
         for (int i = c.tid; i < MAXG * PG_SIZE; i += NTHREADS) sm[c.m.priv + i] = 0.f;
         if (c.tid < MAXG * BT) {                 // fold row ranges cached in shared memory (cond_issue reads them every visit)
             const int g = c.tid / BT, f = c.tid % BT;
@@ -980,16 +1001,18 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
             if (stage == 4 && c.cta >= p.nprod5) break;            // only the logits producers run S5
             if (stage > 0 && t == S) break;
             for (int g = c.team; g < G; g += p.T)
-                if (!visit<PROF>(c, t, stage, g)) return;
+                if (!visit<PROF, BF16W>(c, t, stage, g)) return;
         }
     }
     if (PROF && p.prof && c.tid == 0)
         for (int i = 0; i < PROF_SLOTS; ++i) p.prof[(size_t)c.cta * PROF_SLOTS + i] = reinterpret_cast<long long *>(sm + c.m.prof)[i];
 }
 
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel(const KParams prm) { persistent_body<false>(prm); }
+extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel(const KParams prm) { persistent_body<false, false>(prm); }
+// bf16-weight variant (WRNN_PREC_BF16): same loop, item images hold bf16, fp32 FFMA2 arithmetic
+extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel_bf16w(const KParams prm) { persistent_body<false, true>(prm); }
 // same kernel with the per-stage clock64 accounting compiled in (wrnn_set_profiling)
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel_prof(const KParams prm) { persistent_body<true>(prm); }
+extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel_prof(const KParams prm) { persistent_body<true, false>(prm); }
 
 // Exchange microbenchmark: the same publish / LL-gather sequence on an otherwise empty kernel (one team).
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe_kernel(const KParams prm)
@@ -998,7 +1021,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe
     Ctx c;
     c.p = &prm;
     c.sm = sm;
-    c.m = smem_map(prm.rows5, prm.mode, prm.C, 1, 1);
+    c.m = smem_map(prm.rows5, prm.mode, prm.C, 1, 1, prm.bf16w);
     c.tid = threadIdx.x;
     c.lane = c.tid & 31;
     c.warp = c.tid >> 5;

@@ -175,6 +175,8 @@ class WaveRNN(nn.Module):
         self._feat_dims = feat_dims
         self._fc_dims = fc_dims
         self._engines = {}
+        # "fp32" (default, the reference's precision) or "bf16": resident weights rounded to bf16 (after the fp64
+        # folding of the input layer), activations and accumulation stay fp32.  Set before calling generate().
         self.precision = "fp32"
         self.last_stats = {}
 
@@ -187,11 +189,14 @@ class WaveRNN(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("WaveRNN.generate runs on a CUDA sm_100 device only (no CPU path); got %s" % device)
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        eng = self._engines.get(idx)
+        if self.precision not in _lib.PRECISION:
+            raise ValueError("precision must be one of %s, got %r" % (sorted(_lib.PRECISION), self.precision))
+        key = (idx, self.precision)
+        eng = self._engines.get(key)
         if eng is None:
             cfg = _lib.Config(self.rnn_dims, self._fc_dims, self._feat_dims, self.aux_dims, self.n_classes,
                               _lib.MODE[self.mode], _lib.PRECISION[self.precision])
-            eng = self._engines[idx] = _Engine(cfg, idx)
+            eng = self._engines[key] = _Engine(cfg, idx)
         tag = self._weights_tag()
         if eng.weights_tag != tag:
             eng.load(self.state_dict(), tag)

@@ -258,3 +258,39 @@ def test_mol_in_kernel_rng_and_bits10():
     mf, af = H.folded_conditioning(sd, mel, "ref", True, 700, 60)
     nbad, worst = H.check_raw_labels_consistent(sd, mf[:2], af[:2], U.numpy()[:, :2], lab[:2])
     assert nbad == 0, (nbad, worst)
+
+
+# ---------------------------------------------------------------------------------------------
+# precision="bf16": resident weights rounded to bf16, fp32 activations / accumulation (config 3 of BASELINE.json)
+# ---------------------------------------------------------------------------------------------
+TOL_LOGITS_BF16 = 3e-2          # bf16-weight mode, teacher-forced logits, absolute
+
+
+@pytest.mark.parametrize("mode", ["RAW", "MOL"])
+def test_bf16_weights_teacher_forced_logits_and_free_running(mode):
+    sd = synth.make_state(mode, "ref", 0)
+    m = WaveRNN(**synth.model_kwargs(mode, "ref"))
+    m.load_state_dict(sd)
+    m.cuda()
+    m.precision = "bf16"
+    rng = np.random.default_rng(11)
+    B, S = 11, 48
+    mels = rng.uniform(0, 1, (B, S, 80)).astype(np.float32)
+    aux = rng.normal(0, 1, (B, S, 128)).astype(np.float32)
+    forced = rng.uniform(-1, 1, (S, B)).astype(np.float32)
+    U = synth.make_uniforms(S, B, mode, seed=4).numpy()
+    want = c_oracle.generate_folds(sd, mode, mels, aux, U, forced_x=forced, want_logits=True, precision="fp64")["logits"]
+    got = run_folds(m, mels, aux, U, forced=forced, logits=True)["logits"]
+    err = np.abs(got - want).max()
+    cos = float((got * want).sum() / np.sqrt((got * got).sum() * (want * want).sum()))
+    assert 1e-6 < err <= TOL_LOGITS_BF16, err             # > 1e-6: the bf16 images are really in use
+    assert cos > 0.9999, cos
+    # the same model in fp32 on the same inputs stays at fp32 accuracy (separate engine per precision)
+    m.precision = "fp32"
+    got32 = run_folds(m, mels, aux, U, forced=forced, logits=True)["logits"]
+    assert np.abs(got32 - want).max() <= H.TOL_LOGITS_FP32
+    # free-running generate() in bf16: finite, in range, right length
+    m.precision = "bf16"
+    mel = synth.make_mel(40, seed=2)
+    wav = m.generate(mel, True, 1500, 150, True, seed=3)
+    assert wav.shape == ((40 - 1) * 200,) and np.isfinite(wav).all() and np.abs(wav).max() <= 1.0 + 1e-9
