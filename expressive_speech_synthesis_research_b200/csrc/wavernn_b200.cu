@@ -153,7 +153,7 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
         return fail(WRNN_ERR_CUDA, "persistent kernel does not fit on an SM");
     }
     H_TRY(cudaMalloc(&h->wimg, (size_t)NCTA * w_image_floats(rows5, h->bf16w) * sizeof(float)));
-    H_TRY(cudaMalloc(&h->xb, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long) + (1 << 20)));
+    H_TRY(cudaMalloc(&h->xb, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long) ));
     H_TRY(cudaMalloc(&h->status, 4 * sizeof(int)));
     H_TRY(cudaEventCreate(&h->ev0));
     H_TRY(cudaEventCreate(&h->ev1));
@@ -392,16 +392,10 @@ static int32_t launch_chunk(wrnn_handle *h, KParams &p, cudaStream_t st, bool pr
             if (smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, p.T, 2, h->bf16w).total * (int)sizeof(float) > h->smem_limit) p.nbuf = 1;
         }
     }
-    {
-        const char *sg = getenv("WRNN_STAGGER_CYCLES");     // development knob
-        p.stagger = sg ? atoi(sg) : 6000;
-        const char *pm = getenv("WRNN_POLL_MODE");
-        p.poll_mode = pm ? atoi(pm) : 0;
-    }
     h->smem_bytes = smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, p.T, p.nbuf, h->bf16w).total * (int)sizeof(float);
     h->last_teams = p.T;
     // epochs restart at 1 every launch: clear stale {value, epoch} pairs of the previous one
-    CUDA_TRY(cudaMemsetAsync(h->xb, 0, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long) + (1 << 20), st));
+    CUDA_TRY(cudaMemsetAsync(h->xb, 0, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long), st));
     CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     const void *fn = probe ? (const void *)wavernn_exchange_probe_kernel
@@ -426,10 +420,7 @@ static void fill_common(wrnn_handle *h, KParams &p)
 {
     memset(&p, 0, sizeof p);
     p.wimg = h->wimg;
-    {
-        const char *sh = getenv("WRNN_XB_SHIFT");            // development: shift the exchange buffers by N x 256 B (L2 slice hash experiments)
-        p.xb = h->xb + (sh ? (size_t)(atoi(sh) & 4095) * 32 : 0);
-    }
+    p.xb = h->xb;
     p.status = h->status;
     p.C = h->cfg.n_classes;
     p.mode = h->cfg.mode;

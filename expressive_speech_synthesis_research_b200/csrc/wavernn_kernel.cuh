@@ -104,8 +104,6 @@ struct KParams {
     int feat, auxw;                    // 80, 128
     int T, nbuf;                       // teams per CTA, conditioning staging buffers per team
     int bf16w;                         // 1: item images hold bf16 weights (precision bf16), else fp32
-    int stagger;                       // start-up delay per team index (cycles): breaks the lockstep of the teams
-    int poll_mode;                     // 1: one warp per team polls a sentinel pair per producer, the others wait at a barrier
     int group_fold0[MAXG], group_nf[MAXG];
     int probe_iters;
     long long *prof;                   // optional [NCTA][PROF_SLOTS] per-stage cycle counters (clock64, team 0 thread 0)
@@ -360,27 +358,6 @@ __device__ __forceinline__ void poll_timeout(Ctx &c)
     atomicExch(c.p->status, -4);
 }
 
-// Single-warp wait (poll_mode 1): the last warp of the team polls ONE sentinel pair per producer CTA (the last
-// pair that producer publishes) and the rest of the team sleeps at the barrier.  64x fewer requests hammer L2
-// while the producers are still computing, which shortens the round trip of the loads that matter.
-__device__ __forceinline__ void wait_ready(Ctx &c, const unsigned long long *first, int stride, int nprod, unsigned epoch)
-{
-    if (c.tw == c.nw - 1) {
-        for (int q = c.lane; q < nprod; q += 32) {
-            const unsigned long long *sp = first + (size_t)q * stride;
-            uint2 v = ld_pair(sp);
-            for (int spin = 0; v.y != epoch; ++spin) {
-                if (spin > POLL_CAP) {
-                    poll_timeout(c);
-                    break;
-                }
-                v = ld_pair(sp);
-            }
-        }
-    }
-    team_sync(c);
-}
-
 // LL gather of one exchanged vector (VEC {value, epoch} pairs, [k][8] in L2) into the team's staging
 // buffer.  Every thread polls 16-byte chunks (two pairs) in batches of four until both epochs match.
 // Team-uniform result: false = the watchdog fired somewhere in this team (the kernel then exits and the
@@ -391,8 +368,6 @@ __device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src
     float *dst = c.stage;
     constexpr int NCH = VEC / 2;
     tick<PROF>(c, prof_slot + 4);                // everything between the previous phase and the first poll
-    if (c.p->poll_mode == 1) wait_ready(c, src + 31, 32, NCTA, epoch);
-    if (c.p->poll_mode == 2) team_sync(c);       // nobody polls before this CTA has published its own line
 #pragma unroll 1
     for (int base = c.ttid; base < NCH; base += 4 * c.nt) {
         uint4 v[4];
@@ -480,7 +455,11 @@ __device__ __forceinline__ void cond_issue_next(Ctx &c)
 __device__ __forceinline__ void cond_wait(Ctx &c)
 {
     uint64_t *bar = c.mbar + c.cv_buf;
-    while (!mbar_try_wait(bar, (unsigned)c.cv_par)) {
+    for (int spin = 0; !mbar_try_wait(bar, (unsigned)c.cv_par); ++spin) {
+        if (spin > POLL_CAP) {                   // a conditioning copy never completed (bad pointer?): give up loudly
+            poll_timeout(c);
+            break;
+        }
     }
 }
 
@@ -813,10 +792,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
         if (t > 0) {
             // sample step t-1 from its logits (epoch t).  The barrier orders the draws committed at S4 (CTAs that
             // do not produce logits come here straight from S4's finalize).
-            if (p.poll_mode == 1)
-                wait_ready(c, xb + XB_LG + (size_t)(BT - 1) * (p.rows5 * p.nprod5) + (p.rows5 - 1), p.rows5, p.nprod5, (unsigned)t);
-            else
-                team_sync(c);
+            team_sync(c);
             if (p.mode != 0) sample_mol(c, g, t - 1, (unsigned)t);
             else switch (p.C) {
                 case 1024: sample_raw<32>(c, g, t - 1, (unsigned)t); break;
@@ -884,6 +860,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     }
     if (stage != 3 || cond_live) run_deferred<BF16W>(c, stage);
     team_sync(c);
+    if (*c.abort_flag) return false;
     tick<PROF>(c, 16 + (stage - 1));
     if (stage == 3) {
         // the staging buffer of this conditioning visit is free again: refill it for visit v + nbuf
@@ -985,13 +962,6 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
     if (c.tw == c.nw - 1)
         for (int v = 0; v < p.nbuf; ++v) cond_issue_next(c);
 
-    if (c.team > 0 && p.stagger > 0) {
-        // Teams that start together stay in lockstep (all in their mat-vecs, then all waiting on an exchange);
-        // a one-time offset lets one team's exchange latency hide behind the others' math.
-        const long long t0 = clock64(), wait = (long long)c.team * p.stagger;
-        while (clock64() - t0 < wait) {
-        }
-    }
     if (PROF && c.tid == 0) c.tprev = clock64();
     // t = -1 is the warm-up pass: only the conditioning half of stage 3 runs (projections of step 0).
     // Visit order inside a team: stage-major, its groups inside each stage, so that with several groups

@@ -25,12 +25,8 @@ def main():
     m.cuda()
     eng = m._engine(dev)
     S = 3000
-    cases = [(8, None, 0)]
-    for B, force, stagger in cases:
-        os.environ["WRNN_POLL_MODE"] = str(-stagger) if -10 < stagger < 0 else "0"
-        os.environ["WRNN_DEBUG"] = str(-stagger - 100) if -1000 < stagger <= -100 else "0"
-        os.environ["WRNN_XB_SHIFT"] = str(-stagger - 1000) if stagger <= -1000 else "0"
-        os.environ["WRNN_STAGGER_CYCLES"] = str(max(stagger, 0))
+    cases = [(8, None), (14, None), (20, None), (20, "1"), (64, None)]      # (folds, WRNN_FORCE_TEAMS cap or None)
+    for B, force in cases:
         if force is None:
             os.environ.pop("WRNN_FORCE_TEAMS", None)
         else:
@@ -44,7 +40,7 @@ def main():
             for _ in range(2):
                 m._run_folds(eng, dev, mu, au, starts, starts + L, S, None, 1, None, False)
             ms = eng.info().last_kernel_ms
-            print("B=%d G=%d teams<=%s stagger=%d profiling=%s: %.3f ms, %.2f us/step" % (B, (B + 7) // 8, force or "3", stagger, prof, ms, ms * 1e3 / S), flush=True)
+            print("B=%d G=%d teams<=%s profiling=%s: %.3f ms, %.2f us/step" % (B, (B + 7) // 8, force or "3", prof, ms, ms * 1e3 / S), flush=True)
         cyc = eng.stage_cycles().astype(np.float64) / S
         G = (B + 7) // 8
         tot = cyc[:, :28].sum(1)
