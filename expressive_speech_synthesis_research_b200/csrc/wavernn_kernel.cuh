@@ -783,9 +783,9 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     const float *sv = small(c);
     const float *part = c.part;
     const bool warm = t < 0;
-    // The refill of a conditioning staging buffer costs its issuing warp ~1400 cycles; unless the very next visit
-    // of this team needs the buffer (one buffer, several groups) it is postponed to the deferred phase of S2.
-    const bool late_issue = p.nbuf == 2 || c.ng == 1;
+    // The refill of a conditioning staging buffer costs its issuing warp ~1400 cycles; unless this team's next visits
+    // need the buffer before S2 comes round again (more groups than buffers) it is postponed to S2's deferred phase.
+    const bool late_issue = c.ng <= p.nbuf;
 
     if (warm) team_sync(c);                              // no gather barrier in the warm-up pass: part is reused
     if (stage == 0) {

@@ -294,3 +294,20 @@ def test_bf16_weights_teacher_forced_logits_and_free_running(mode):
     mel = synth.make_mel(40, seed=2)
     wav = m.generate(mel, True, 1500, 150, True, seed=3)
     assert wav.shape == ((40 - 1) * 200,) and np.isfinite(wav).all() and np.abs(wav).max() <= 1.0 + 1e-9
+
+
+def test_results_do_not_depend_on_the_team_layout(monkeypatch):
+    """The host picks how many teams share a CTA (1-3, development cap WRNN_FORCE_TEAMS); work is dealt to warps in
+    fixed items / units and partial sums are combined in a fixed order, so samples must be bit-identical."""
+    m = model("RAW")
+    rng = np.random.default_rng(3)
+    B, S = 20, 40
+    mels = rng.uniform(0, 1, (B, S, 80)).astype(np.float32)
+    aux = rng.normal(0, 1, (B, S, 128)).astype(np.float32)
+    U = synth.make_uniforms(S, B, "RAW", seed=8).numpy()
+    monkeypatch.delenv("WRNN_FORCE_TEAMS", raising=False)
+    ref = run_folds(m, mels, aux, U, logits=True)
+    for cap in ("1", "2"):
+        monkeypatch.setenv("WRNN_FORCE_TEAMS", cap)
+        got = run_folds(m, mels, aux, U, logits=True)
+        assert np.array_equal(got["labels"], ref["labels"]) and np.array_equal(got["logits"], ref["logits"]), cap
