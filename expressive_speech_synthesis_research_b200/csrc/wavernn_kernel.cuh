@@ -362,25 +362,25 @@ __device__ __forceinline__ void poll_timeout(Ctx &c)
 // buffer.  Every thread polls 16-byte chunks (two pairs) in batches of four until both epochs match.
 // Team-uniform result: false = the watchdog fired somewhere in this team (the kernel then exits and the
 // host reports WRNN_ERR_TIMEOUT).
-template <bool PROF>
+template <bool PROF, int BATCH>
 __device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src, unsigned epoch, int prof_slot = 19)
 {
     float *dst = c.stage;
     constexpr int NCH = VEC / 2;
     tick<PROF>(c, prof_slot + 4);                // everything between the previous phase and the first poll
 #pragma unroll 1
-    for (int base = c.ttid; base < NCH; base += 4 * c.nt) {
-        uint4 v[4];
-        bool need[4];
+    for (int base = c.ttid; base < NCH; base += BATCH * c.nt) {
+        uint4 v[BATCH];
+        bool need[BATCH];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < BATCH; ++j) {
             need[j] = base + j * c.nt < NCH;
             if (need[j]) v[j] = ld_pairs2(src + 2 * (base + j * c.nt));
         }
         for (int spin = 0;; ++spin) {
             bool bad = false;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < BATCH; ++j) {
                 const bool b = need[j] && ((v[j].y != epoch) | (v[j].w != epoch));
                 if (b) v[j] = ld_pairs2(src + 2 * (base + j * c.nt));
                 bad |= b;
@@ -392,7 +392,7 @@ __device__ __forceinline__ bool gather_vec(Ctx &c, const unsigned long long *src
             }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < BATCH; ++j) {
             if (!need[j]) continue;
             const int i = base + j * c.nt, k = i >> 2, f0 = (i & 3) * 2;
             // folds f0, f0+1 live in slots (f0 ^ (k&3)), (f0+1) ^ (k&3): an aligned pair, swapped when k is odd
@@ -772,7 +772,7 @@ __device__ __forceinline__ void gru_publish(Ctx &c, float *pg, unsigned long lon
 }
 
 // One visit: stage `stage` of step t for group g.  Returns false when the watchdog fired (team-uniform).
-template <bool PROF, bool BF16W>
+template <bool PROF, bool BF16W, int BATCH>
 __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
 {
     const KParams &p = *c.p;
@@ -817,7 +817,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     const bool cond_live = t + 1 < S;
     const int rows5 = p.rows5;
     if (!warm && stage > 0) {
-        if (!gather_vec<PROF>(c, xb + (stage - 1) * VEC, epoch, 19 + stage)) return false;   // H1 | H2 | Y1 | Y2
+        if (!gather_vec<PROF, BATCH>(c, xb + (stage - 1) * VEC, epoch, 19 + stage)) return false;   // H1 | H2 | Y1 | Y2
         tick<PROF>(c, 3 * stage + (stage >= 3 ? 1 : 0));
         run_critical<BF16W>(c, stage);
         team_sync(c);
@@ -890,7 +890,9 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     return true;
 }
 
-template <bool PROF, bool BF16W>
+// TEAMS is a compile-time constant (one kernel per team count): warps / threads per team fold into immediates
+// and the gather can keep the right number of polls in flight.
+template <bool PROF, bool BF16W, int TEAMS>
 __device__ __forceinline__ void persistent_body(const KParams &prm)
 {
     extern __shared__ __align__(128) float sm[];
@@ -898,21 +900,22 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
     Ctx c;
     c.p = &prm;
     c.sm = sm;
-    c.m = smem_map(p.rows5, p.mode, p.C, p.T, p.nbuf, BF16W ? 1 : 0);
+    c.m = smem_map(p.rows5, p.mode, p.C, TEAMS, p.nbuf, BF16W ? 1 : 0);
     c.tid = threadIdx.x;
     c.lane = c.tid & 31;
     c.warp = c.tid >> 5;
     c.cta = blockIdx.x;
-    c.nw = team_warps(p.T);
+    c.nw = team_warps(TEAMS);
     c.nt = c.nw * 32;
+    constexpr int BATCH = TEAMS == 1 ? 4 : TEAMS == 2 ? 8 : 7;
     c.team = c.warp / c.nw;
     c.tw = c.warp - c.team * c.nw;
     c.ttid = c.tid - c.team * c.nt;
     c.cv_buf = c.cv_par = 0;
     c.is_step = c.is_buf = 0;
     c.tprev = 0;
-    const bool member = c.team < p.T;
-    c.ng = member ? (p.G - c.team + p.T - 1) / p.T : 0;
+    const bool member = c.team < TEAMS;
+    c.ng = member ? (p.G - c.team + TEAMS - 1) / TEAMS : 0;
     c.is_g = c.team;
     {
         float *tb = sm + c.m.team0 + (member ? c.team : 0) * c.m.team_stride;
@@ -938,7 +941,7 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
             fs[c.tid] = live ? p.fold_start[p.group_fold0[g] + f] : 0;
             fs[MAXG * BT + c.tid] = live ? p.fold_limit[p.group_fold0[g] + f] : 0;
         }
-        if (c.tid < p.T) {
+        if (c.tid < TEAMS) {
             float *tb = sm + c.m.team0 + c.tid * c.m.team_stride;
             uint64_t *bar = reinterpret_cast<uint64_t *>(tb + c.m.t_ctl);
             mbar_init(bar, 1);
@@ -970,19 +973,29 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
         for (int stage = (t < 0 ? 3 : 0); stage < (t < 0 ? 4 : 5); ++stage) {
             if (stage == 4 && c.cta >= p.nprod5) break;            // only the logits producers run S5
             if (stage > 0 && t == S) break;
-            for (int g = c.team; g < G; g += p.T)
-                if (!visit<PROF, BF16W>(c, t, stage, g)) return;
+            for (int g = c.team; g < G; g += TEAMS)
+                if (!visit<PROF, BF16W, BATCH>(c, t, stage, g)) return;
         }
     }
     if (PROF && p.prof && c.tid == 0)
         for (int i = 0; i < PROF_SLOTS; ++i) p.prof[(size_t)c.cta * PROF_SLOTS + i] = reinterpret_cast<long long *>(sm + c.m.prof)[i];
 }
 
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel(const KParams prm) { persistent_body<false, false>(prm); }
-// bf16-weight variant (WRNN_PREC_BF16): same loop, item images hold bf16, fp32 FFMA2 arithmetic
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel_bf16w(const KParams prm) { persistent_body<false, true>(prm); }
-// same kernel with the per-stage clock64 accounting compiled in (wrnn_set_profiling)
-extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_persistent_kernel_prof(const KParams prm) { persistent_body<true, false>(prm); }
+#define WRNN_KERNEL(name, PROF, BF16W, TEAMS) \
+    extern "C" __global__ void __launch_bounds__(NTHREADS, 1) name(const KParams prm) { persistent_body<PROF, BF16W, TEAMS>(prm); }
+// fp32 images, 1 / 2 / 3 teams per CTA
+WRNN_KERNEL(wavernn_persistent_kernel, false, false, 1)
+WRNN_KERNEL(wavernn_persistent_kernel_t2, false, false, 2)
+WRNN_KERNEL(wavernn_persistent_kernel_t3, false, false, 3)
+// bf16-weight variants (WRNN_PREC_BF16): same loop, item images hold bf16, fp32 FFMA2 arithmetic
+WRNN_KERNEL(wavernn_persistent_kernel_bf16w, false, true, 1)
+WRNN_KERNEL(wavernn_persistent_kernel_bf16w_t2, false, true, 2)
+WRNN_KERNEL(wavernn_persistent_kernel_bf16w_t3, false, true, 3)
+// fp32 with the per-stage clock64 accounting compiled in (wrnn_set_profiling)
+WRNN_KERNEL(wavernn_persistent_kernel_prof, true, false, 1)
+WRNN_KERNEL(wavernn_persistent_kernel_prof_t2, true, false, 2)
+WRNN_KERNEL(wavernn_persistent_kernel_prof_t3, true, false, 3)
+#undef WRNN_KERNEL
 
 // Exchange microbenchmark: the same publish / LL-gather sequence on an otherwise empty kernel (one team).
 extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe_kernel(const KParams prm)
@@ -1013,7 +1026,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe
         unsigned long long *vec = xb + (it & 3) * VEC;
         const unsigned epoch = (unsigned)it + 1u;
         if (c.warp == 0) publish_line(vec, c.cta, c.lane, acc + (float)it, epoch);
-        if (!gather_vec<false>(c, vec, epoch)) return;
+        if (!gather_vec<false, 4>(c, vec, epoch)) return;
         acc += c.stage[c.tid] * 1e-30f;
         __syncthreads();
     }
