@@ -102,16 +102,19 @@ static int32_t derive_layout(const wrnn_config &c, int &rows5, int &nprod5, int 
     return WRNN_OK;
 }
 
-// one kernel per (teams per CTA, weight image precision, profiling); profiling exists for fp32 images only
-static const void *persistent_kernel(int T, int bf16w, int prof)
+// one kernel per (teams per CTA, model geometry, weight image precision); profiling exists for the generic fp32 kernels
+#define K3(stem) {(const void *)stem, (const void *)stem##_t2, (const void *)stem##_t3}
+static const void *persistent_kernel(int T, int model, int bf16w, int prof)
 {
-    static const void *tab[2][2][MAXT] = {
-        {{(const void *)wavernn_persistent_kernel, (const void *)wavernn_persistent_kernel_t2, (const void *)wavernn_persistent_kernel_t3},
-         {(const void *)wavernn_persistent_kernel_prof, (const void *)wavernn_persistent_kernel_prof_t2, (const void *)wavernn_persistent_kernel_prof_t3}},
-        {{(const void *)wavernn_persistent_kernel_bf16w, (const void *)wavernn_persistent_kernel_bf16w_t2, (const void *)wavernn_persistent_kernel_bf16w_t3},
-         {nullptr, nullptr, nullptr}}};
-    return tab[bf16w ? 1 : 0][prof ? 1 : 0][T - 1];
+    static const void *plain[3][2][MAXT] = {{K3(wavernn_persistent_kernel_any), K3(wavernn_persistent_kernel_any_bf16w)},
+                                            {K3(wavernn_persistent_kernel), K3(wavernn_persistent_kernel_bf16w)},
+                                            {K3(wavernn_persistent_kernel_mol), K3(wavernn_persistent_kernel_mol_bf16w)}};
+    static const void *profk[MAXT] = K3(wavernn_persistent_kernel_prof);
+    if (prof && !bf16w) return profk[T - 1];
+    return plain[model][bf16w ? 1 : 0][T - 1];
 }
+#undef K3
+static int model_of(const wrnn_config &c) { return c.mode == WRNN_MODE_MOL ? 2 : c.n_classes == 512 ? 1 : 0; }
 
 extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_handle **out)
 {
@@ -153,12 +156,12 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
         wrnn_destroy(h);                                                             \
         return fail(WRNN_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e));          \
     }
-    for (int bf = 0; bf < 2; ++bf)
-        for (int pr = 0; pr < 2 - bf; ++pr)
-            for (int T = 1; T <= MAXT; ++T) H_TRY(cudaFuncSetAttribute(persistent_kernel(T, bf, pr), cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_limit));
+    for (int pr = 0; pr < 2; ++pr)
+        for (int T = 1; T <= MAXT; ++T)
+            H_TRY(cudaFuncSetAttribute(persistent_kernel(T, model_of(*cfg), h->bf16w, pr), cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_limit));
     H_TRY(cudaFuncSetAttribute(wavernn_exchange_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem_limit));
     int occ = 0;
-    H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, wavernn_persistent_kernel, NTHREADS, h->smem_bytes));
+    H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, persistent_kernel(1, model_of(*cfg), h->bf16w, 0), NTHREADS, h->smem_bytes));
     if (occ < 1) {
         wrnn_destroy(h);
         return fail(WRNN_ERR_CUDA, "persistent kernel does not fit on an SM");
@@ -410,7 +413,7 @@ static int32_t launch_chunk(wrnn_handle *h, KParams &p, cudaStream_t st, bool pr
     CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
     CUDA_TRY(cudaEventRecord(h->ev0, st));
     const void *fn = probe ? (const void *)wavernn_exchange_probe_kernel
-                           : persistent_kernel(p.T, h->bf16w, p.prof != nullptr && !h->bf16w);
+                           : persistent_kernel(p.T, model_of(h->cfg), h->bf16w, p.prof != nullptr);
     CUDA_TRY(cudaLaunchCooperativeKernel(fn,
                                          dim3(NCTA), dim3(NTHREADS), args, (size_t)h->smem_bytes, st));
     CUDA_TRY(cudaEventRecord(h->ev1, st));

@@ -323,6 +323,7 @@ struct Ctx {
     float *sm;
     SmemMap m;
     int tid, lane, warp, cta;
+    int C, rows5, nprod5, mode;       // model geometry: compile-time constants in the specialised kernels (MODEL 1, 2)
     int team, nw, nt, tw, ttid, ng;   // team index, warps / threads per team, warp / thread inside the team, groups of this team
     float *stage, *part, *cst;        // this team's staging buffers
     uint64_t *mbar;                   // this team's two conditioning mbarriers
@@ -345,10 +346,10 @@ __device__ __forceinline__ void tick(Ctx &c, int slot)
 }
 
 __device__ __forceinline__ float *priv(const Ctx &c, int g) { return c.sm + c.m.priv + g * PG_SIZE; }
-__device__ __forceinline__ const float *small(const Ctx &c) { return c.sm + c.m.w + (w_image_floats(c.p->rows5, c.p->bf16w) - SV_SIZE); }
+__device__ __forceinline__ const float *small(const Ctx &c) { return c.sm + c.m.w + (w_image_floats(c.rows5, c.p->bf16w) - SV_SIZE); }
 __device__ __forceinline__ unsigned long long *xb_base(const Ctx &c, int g)
 {
-    return c.p->xb + (size_t)g * xb_group(c.p->rows5 * c.p->nprod5);
+    return c.p->xb + (size_t)g * xb_group(c.rows5 * c.nprod5);
 }
 __device__ __forceinline__ void team_sync(const Ctx &c) { bar_team(1 + c.team, c.nt); }
 
@@ -601,9 +602,9 @@ __device__ __forceinline__ void sample_mol(Ctx &c, int g, int s, unsigned epoch)
     float *lg = c.stage;
     float *pg = priv(c, g);
     const int lane = c.lane, f = lane & 7, cs = lane >> 3;
-    const int nr = p.C / 3, cpad = p.rows5 * p.nprod5;
+    const int nr = c.C / 3, cpad = c.rows5 * c.nprod5;
     const unsigned long long *src = xb_base(c, g) + XB_LG + (size_t)f * cpad;
-    for (int i = cs; i < p.C; i += 4) {
+    for (int i = cs; i < c.C; i += 4) {
         uint2 v = ld_pair(src + i);
         for (int spin = 0; v.y != epoch; ++spin) {
             if (spin > POLL_CAP) {
@@ -655,10 +656,10 @@ __device__ __forceinline__ void dump_logits(Ctx &c, int g, int s)
     const KParams &p = *c.p;
     if (c.cta != (s * p.G + g) % NCTA) return;
     const float *lg = c.stage;
-    const int npl = p.mode == 0 ? p.C >> 5 : 0;
+    const int npl = c.mode == 0 ? c.C >> 5 : 0;
     for (int f = 0; f < p.group_nf[g]; ++f) {
-        float *dst = p.logits_out + ((size_t)s * p.B + p.group_fold0[g] + f) * p.C;
-        for (int k = c.ttid; k < p.C; k += c.nt) dst[k] = npl ? lg[f * p.C + lg_pos_dyn(npl, k)] : lg[k * BT + f];
+        float *dst = p.logits_out + ((size_t)s * p.B + p.group_fold0[g] + f) * c.C;
+        for (int k = c.ttid; k < c.C; k += c.nt) dst[k] = npl ? lg[f * c.C + lg_pos_dyn(npl, k)] : lg[k * BT + f];
     }
 }
 
@@ -691,7 +692,7 @@ template <bool BF16W>
 __device__ __forceinline__ void run_critical(Ctx &c, int stage)
 {
     constexpr int SH = BF16W ? 1 : 0;            // item offsets halve when the images hold bf16
-    const int rows5 = c.p->rows5;
+    const int rows5 = c.rows5;
     const int n = stage == 1 ? 12 : stage == 4 ? rows5 : 4;
     const int woff = stage == 1 ? W_M2 : stage == 2 ? W_M3 : stage == 3 ? W_M4 : W_M5;
     const float *W = c.sm + c.m.w + (woff >> SH);
@@ -708,7 +709,7 @@ template <bool BF16W>
 __device__ __forceinline__ void run_deferred(Ctx &c, int stage)
 {
     constexpr int SH = BF16W ? 1 : 0;
-    const int rows5 = c.p->rows5;
+    const int rows5 = c.rows5;
     const int n = stage == 1 ? 8 : stage == 2 ? 6 : 8;
     const float *W = c.sm + c.m.w;
     // deal from warp 1 on: warp 0 is busy with the pointwise math + publish of this stage
@@ -793,8 +794,8 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
             // sample step t-1 from its logits (epoch t).  The barrier orders the draws committed at S4 (CTAs that
             // do not produce logits come here straight from S4's finalize).
             team_sync(c);
-            if (p.mode != 0) sample_mol(c, g, t - 1, (unsigned)t);
-            else switch (p.C) {
+            if (c.mode != 0) sample_mol(c, g, t - 1, (unsigned)t);
+            else switch (c.C) {
                 case 1024: sample_raw<32>(c, g, t - 1, (unsigned)t); break;
                 case 512: sample_raw<16>(c, g, t - 1, (unsigned)t); break;
                 case 256: sample_raw<8>(c, g, t - 1, (unsigned)t); break;
@@ -815,7 +816,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
     // stages 1..4: gather + critical items, then pointwise math + publish, then the deferred units inside the
     // exchange latency of the value just published (SA has no mat-vec work: GRU1's input side is all precomputed).
     const bool cond_live = t + 1 < S;
-    const int rows5 = p.rows5;
+    const int rows5 = c.rows5;
     if (!warm && stage > 0) {
         if (!gather_vec<PROF, BATCH>(c, xb + (stage - 1) * VEC, epoch, 19 + stage)) return false;   // H1 | H2 | Y1 | Y2
         tick<PROF>(c, 3 * stage + (stage >= 3 ? 1 : 0));
@@ -847,7 +848,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
             for (int role = tw; role < (rows5 >> 2); role += nw) {
                 const float v = sum4(part, role, lane) + sv[SV_B5 + role * 4 + (lane >> 3)];
                 const int k = rows5 * c.cta + role * 4 + (lane >> 3);
-                st_pair(xb + XB_LG + (size_t)(lane & 7) * (rows5 * p.nprod5) + k, v, epoch);
+                st_pair(xb + XB_LG + (size_t)(lane & 7) * (rows5 * c.nprod5) + k, v, epoch);
             }
             tick<PROF>(c, 15);
             return true;
@@ -892,7 +893,7 @@ __device__ __forceinline__ bool visit(Ctx &c, int t, int stage, int g)
 
 // TEAMS is a compile-time constant (one kernel per team count): warps / threads per team fold into immediates
 // and the gather can keep the right number of polls in flight.
-template <bool PROF, bool BF16W, int TEAMS>
+template <bool PROF, bool BF16W, int TEAMS, int MODEL>
 __device__ __forceinline__ void persistent_body(const KParams &prm)
 {
     extern __shared__ __align__(128) float sm[];
@@ -900,7 +901,12 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
     Ctx c;
     c.p = &prm;
     c.sm = sm;
-    c.m = smem_map(p.rows5, p.mode, p.C, TEAMS, p.nbuf, BF16W ? 1 : 0);
+    // MODEL 1 = RAW with 512 classes, 2 = MOL (30 logits): geometry folds into immediates; 0 = any supported model
+    c.C = MODEL == 1 ? 512 : MODEL == 2 ? 30 : p.C;
+    c.rows5 = MODEL ? 4 : p.rows5;
+    c.nprod5 = MODEL == 1 ? 128 : MODEL == 2 ? 8 : p.nprod5;
+    c.mode = MODEL == 1 ? 0 : MODEL == 2 ? 1 : p.mode;
+    c.m = smem_map(c.rows5, c.mode, c.C, TEAMS, p.nbuf, BF16W ? 1 : 0);
     c.tid = threadIdx.x;
     c.lane = c.tid & 31;
     c.warp = c.tid >> 5;
@@ -929,7 +935,7 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
 
     // ---- prologue (whole CTA): resident weights, zero state ------------------------------------
     {
-        const int wfloats = w_image_floats(p.rows5, BF16W ? 1 : 0);
+        const int wfloats = w_image_floats(c.rows5, BF16W ? 1 : 0);
         const float4 *src = reinterpret_cast<const float4 *>(p.wimg + (size_t)c.cta * wfloats);
         float4 *dst = reinterpret_cast<float4 *>(sm + c.m.w);
         for (int i = c.tid; i < wfloats / 4; i += NTHREADS) dst[i] = src[i];
@@ -971,7 +977,7 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
     // per team one group's exchange still overlaps the others' mat-vecs.
     for (int t = -1; t <= S; ++t) {
         for (int stage = (t < 0 ? 3 : 0); stage < (t < 0 ? 4 : 5); ++stage) {
-            if (stage == 4 && c.cta >= p.nprod5) break;            // only the logits producers run S5
+            if (stage == 4 && c.cta >= c.nprod5) break;            // only the logits producers run S5
             if (stage > 0 && t == S) break;
             for (int g = c.team; g < G; g += TEAMS)
                 if (!visit<PROF, BF16W, BATCH>(c, t, stage, g)) return;
@@ -981,20 +987,20 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
         for (int i = 0; i < PROF_SLOTS; ++i) p.prof[(size_t)c.cta * PROF_SLOTS + i] = reinterpret_cast<long long *>(sm + c.m.prof)[i];
 }
 
-#define WRNN_KERNEL(name, PROF, BF16W, TEAMS) \
-    extern "C" __global__ void __launch_bounds__(NTHREADS, 1) name(const KParams prm) { persistent_body<PROF, BF16W, TEAMS>(prm); }
-// fp32 images, 1 / 2 / 3 teams per CTA
-WRNN_KERNEL(wavernn_persistent_kernel, false, false, 1)
-WRNN_KERNEL(wavernn_persistent_kernel_t2, false, false, 2)
-WRNN_KERNEL(wavernn_persistent_kernel_t3, false, false, 3)
-// bf16-weight variants (WRNN_PREC_BF16): same loop, item images hold bf16, fp32 FFMA2 arithmetic
-WRNN_KERNEL(wavernn_persistent_kernel_bf16w, false, true, 1)
-WRNN_KERNEL(wavernn_persistent_kernel_bf16w_t2, false, true, 2)
-WRNN_KERNEL(wavernn_persistent_kernel_bf16w_t3, false, true, 3)
-// fp32 with the per-stage clock64 accounting compiled in (wrnn_set_profiling)
-WRNN_KERNEL(wavernn_persistent_kernel_prof, true, false, 1)
-WRNN_KERNEL(wavernn_persistent_kernel_prof_t2, true, false, 2)
-WRNN_KERNEL(wavernn_persistent_kernel_prof_t3, true, false, 3)
+#define WRNN_KERNEL(name, PROF, BF16W, TEAMS, MODEL) \
+    extern "C" __global__ void __launch_bounds__(NTHREADS, 1) name(const KParams prm) { persistent_body<PROF, BF16W, TEAMS, MODEL>(prm); }
+#define WRNN_KERNELS3(stem, PROF, BF16W, MODEL) \
+    WRNN_KERNEL(stem, PROF, BF16W, 1, MODEL) WRNN_KERNEL(stem##_t2, PROF, BF16W, 2, MODEL) WRNN_KERNEL(stem##_t3, PROF, BF16W, 3, MODEL)
+// One kernel per (teams per CTA) x (model geometry: RAW-512 | MOL | any) x (fp32 | bf16 weight images); the generic
+// fp32 kernels also exist with the per-stage clock64 accounting compiled in (wrnn_set_profiling).
+WRNN_KERNELS3(wavernn_persistent_kernel, false, false, 1)
+WRNN_KERNELS3(wavernn_persistent_kernel_mol, false, false, 2)
+WRNN_KERNELS3(wavernn_persistent_kernel_any, false, false, 0)
+WRNN_KERNELS3(wavernn_persistent_kernel_bf16w, false, true, 1)
+WRNN_KERNELS3(wavernn_persistent_kernel_mol_bf16w, false, true, 2)
+WRNN_KERNELS3(wavernn_persistent_kernel_any_bf16w, false, true, 0)
+WRNN_KERNELS3(wavernn_persistent_kernel_prof, true, false, 0)
+#undef WRNN_KERNELS3
 #undef WRNN_KERNEL
 
 // Exchange microbenchmark: the same publish / LL-gather sequence on an otherwise empty kernel (one team).
@@ -1004,6 +1010,10 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe
     Ctx c;
     c.p = &prm;
     c.sm = sm;
+    c.C = prm.C;
+    c.rows5 = prm.rows5;
+    c.nprod5 = prm.nprod5;
+    c.mode = prm.mode;
     c.m = smem_map(prm.rows5, prm.mode, prm.C, 1, 1, prm.bf16w);
     c.tid = threadIdx.x;
     c.lane = c.tid & 31;
