@@ -242,13 +242,16 @@ __device__ __forceinline__ void item_fma_cond(const float *wimg, const float *cs
     float4 w[4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) w[r] = ld_w4<BF16W>(wimg, r, lane);
-    const int fx = lane & 7;
+    // register slot s holds fold s ^ (lane & 7); its four k are kbase + lane + 32 i at fixed offsets from one pointer
+    const float *row[BT];
+#pragma unroll
+    for (int s = 0; s < BT; ++s) row[s] = cst + (s ^ (lane & 7)) * CROW + kbase + lane;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int k = kbase + lane + 32 * i;
+        const bool live = kbase + lane + 32 * i < CROW;            // only the tail of chunk B is padding
         float x[BT];
 #pragma unroll
-        for (int s = 0; s < BT; ++s) x[s] = (k < CROW) ? cst[(s ^ fx) * CROW + k] : 0.f;
+        for (int s = 0; s < BT; ++s) x[s] = live ? row[s][32 * i] : 0.f;
         const f32x2 x0 = pack2(x[0], x[1]), x1 = pack2(x[2], x[3]), x2 = pack2(x[4], x[5]), x3 = pack2(x[6], x[7]);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -440,7 +443,10 @@ __device__ __forceinline__ void cond_issue_next(Ctx &c)
         valid = row < fs[MAXG * BT + g * BT + f];
     }
     const unsigned m = __ballot_sync(0xffffffffu, valid) & 0xffu;
-    if (m != 0xffu) cond_zero_rows(buf, m, c.lane);
+    // folds that exist but have run past their conditioning read zeros (rows of folds that do not exist were zeroed
+    // once in the prologue and are never written)
+    const unsigned exist = (1u << p.group_nf[g]) - 1u;
+    if ((m & exist) != exist) cond_zero_rows(buf, m | ~exist, c.lane);
     // the staging buffer was last read through the generic proxy (work items, before the team barrier)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
@@ -956,6 +962,8 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if (c.tid < 2 * PROF_SLOTS) sm[c.m.prof + c.tid] = 0.f;
+        for (int tm = 0; tm < TEAMS; ++tm)         // conditioning staging starts as zeros (rows of absent folds stay so)
+            for (int i = c.tid; i < p.nbuf * BT * CROW; i += NTHREADS) sm[c.m.team0 + tm * c.m.team_stride + c.m.t_cst + i] = 0.f;
         __syncthreads();
         const float *sv = small(c);
         for (int g = 0; g < G; ++g) {           // h = 0  =>  gh = b_hh  (fatchord_version.py:173-174)
