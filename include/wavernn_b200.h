@@ -46,7 +46,8 @@ typedef struct {
     int32_t aux_dims;    /* res_out_dims / 4 = 32 (fatchord_version.py:104) */
     int32_t n_classes;   /* 2**bits (RAW) or 30 (MOL) (fatchord_version.py:96-99) */
     int32_t mode;        /* WRNN_MODE_* */
-    int32_t precision;   /* WRNN_PREC_*: storage of the resident weights / exchanged activations */
+    int32_t precision;   /* WRNN_PREC_*: storage of the RESIDENT WEIGHTS (bf16 = rounded after the fp64 folding of the
+                            input layer); activations, accumulation and the exchange stay fp32 in both */
 } wrnn_config;
 
 /* The sixteen state_dict tensors on the step path, torch [out, in] row-major fp32, HOST memory
