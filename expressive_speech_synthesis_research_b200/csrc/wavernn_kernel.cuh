@@ -520,7 +520,7 @@ __device__ __forceinline__ void sample_raw(Ctx &c, int g, int s, unsigned epoch)
     const int lane = c.lane;
     constexpr int C = NPL * 32;
     constexpr int NCH = (NPL / 2) > 0 ? NPL / 2 : 1;        // 16-byte chunks (2 classes) per lane
-    constexpr int BATCH = NCH < 4 ? NCH : 4;
+    constexpr int BATCH = NPL == 16 ? 8 : (NCH < 4 ? NCH : 4);   // 512 classes: all chunks of a fold in flight (one round trip)
     for (int f = c.tw; f < BT; f += c.nw) {
         const unsigned long long *src = xb_base(c, g) + XB_LG + (size_t)f * C;
         float *row = c.stage + f * C;
