@@ -7,7 +7,7 @@ from . import build as _build
 i32, i64, u64, vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_void_p
 
 MODE = {"RAW": 0, "MOL": 1}
-PRECISION = {"fp32": 0, "bf16": 1}
+PRECISION = {"fp32": 0, "bf16": 1, "bf16-dense": 2}
 
 
 class Config(ctypes.Structure):
@@ -40,6 +40,8 @@ SYMBOLS = {
     "wrnn_load_weights": (i32, [vp, ctypes.POINTER(Weights)]),
     "wrnn_packed_floats": (i64, [ctypes.POINTER(Config)]),
     "wrnn_pack_weights_host": (i32, [ctypes.POINTER(Config), ctypes.POINTER(Weights), vp, i64]),
+    "wrnn_dense_layout": (i32, [ctypes.POINTER(Config), ctypes.POINTER(i64)]),
+    "wrnn_dense_pack_host": (i32, [ctypes.POINTER(Config), ctypes.POINTER(Weights), vp, vp, vp]),
     "wrnn_fold_index": (i32, [i64, i64, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
     "wrnn_generate_folds": (i32, [vp, vp, vp, i64, vp, vp, i32, i32, vp, u64, vp, vp, vp, vp, vp]),
     "wrnn_xfade_unfold": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, vp, vp]),

@@ -2,12 +2,14 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include "../../include/wavernn_b200.h"
 #include "wavernn_kernel.cuh"
+#include "wavernn_dense.cuh"
 
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -51,6 +53,12 @@ struct wrnn_handle {
     float last_ms = 0.f;
     long long *prof_dev = nullptr;   // [NCTA][PROF_SLOTS], allocated by wrnn_set_profiling
     bool profiling = false;
+    // precision bf16-dense (csrc/wavernn_dense.cuh): streamed operand tiles, bundle table, per-row fp32 vectors
+    int dense = 0, dense_nb = 0, dense_clusters = 0;
+    unsigned dense_stream_bytes = 0;
+    unsigned char *dense_stream = nullptr;
+    wrnn_dense::Bundle *dense_table = nullptr;
+    float *dense_sv = nullptr;
 };
 
 extern "C" int32_t wrnn_abi_version(void) { return WRNN_ABI_VERSION; }
@@ -83,8 +91,10 @@ static int32_t derive_layout(const wrnn_config &c, int &rows5, int &nprod5, int 
         return fail(WRNN_ERR_INVALID, "this build keeps rnn_dims == fc_dims == %d resident (got %d / %d)", HID, c.rnn_dims, c.fc_dims);
     if (c.feat_dims != 80 || c.aux_dims != 32)
         return fail(WRNN_ERR_INVALID, "conditioning layout is fixed to feat_dims 80 + 4 x aux_dims 32 (got %d, %d)", c.feat_dims, c.aux_dims);
-    if (c.precision != WRNN_PREC_FP32 && c.precision != WRNN_PREC_BF16)
+    if (c.precision != WRNN_PREC_FP32 && c.precision != WRNN_PREC_BF16 && c.precision != WRNN_PREC_BF16_DENSE)
         return fail(WRNN_ERR_INVALID, "unknown precision %d", c.precision);
+    if (c.precision == WRNN_PREC_BF16_DENSE && !(c.mode == WRNN_MODE_RAW && c.n_classes == wrnn_dense::NCLASS))
+        return fail(WRNN_ERR_INVALID, "precision bf16-dense (tcgen05 path) is built for RAW mode with %d classes", wrnn_dense::NCLASS);
     if (c.mode == WRNN_MODE_RAW) {
         const int C = c.n_classes;
         if (C != 64 && C != 128 && C != 256 && C != 512 && C != 1024)
@@ -171,6 +181,25 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
     H_TRY(cudaMalloc(&h->status, 4 * sizeof(int)));
     H_TRY(cudaEventCreate(&h->ev0));
     H_TRY(cudaEventCreate(&h->ev1));
+    if (cfg->precision == WRNN_PREC_BF16_DENSE) {
+        h->dense = 1;
+        if (wrnn_dense::SM_TOTAL > h->smem_limit) {
+            wrnn_destroy(h);
+            return fail(WRNN_ERR_CUDA, "dense kernel needs %d B shared memory, device allows %d", wrnn_dense::SM_TOTAL, h->smem_limit);
+        }
+        H_TRY(cudaFuncSetAttribute(wrnn_dense::wavernn_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wrnn_dense::SM_TOTAL));
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(wrnn_dense::CL * 64);
+        lc.blockDim = dim3(wrnn_dense::DTHREADS);
+        lc.dynamicSmemBytes = wrnn_dense::SM_TOTAL;
+        int ncl = 0;
+        H_TRY(cudaOccupancyMaxActiveClusters(&ncl, wrnn_dense::wavernn_dense_kernel, &lc));
+        if (ncl < 1) {
+            wrnn_destroy(h);
+            return fail(WRNN_ERR_CUDA, "no cluster of %d CTAs of the dense kernel fits on this device", wrnn_dense::CL);
+        }
+        h->dense_clusters = ncl;
+    }
 #undef H_TRY
     *out = h;
     return WRNN_OK;
@@ -185,6 +214,9 @@ extern "C" void wrnn_destroy(wrnn_handle *h)
     cudaFree(h->status);
     cudaFree(h->fold_dev);
     cudaFree(h->prof_dev);
+    cudaFree(h->dense_stream);
+    cudaFree(h->dense_table);
+    cudaFree(h->dense_sv);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -341,6 +373,227 @@ static void finish_images(int rows5, int bf16w, const std::vector<float> &img32,
     }
 }
 
+// ---- precision bf16-dense: operand stream, bundle table and per-row vectors of csrc/wavernn_dense.cuh ------------
+// One step of the tensor-core program, in issue order (wavernn_dense.cuh has the dependency argument):
+//   (a) after h1(t):  Wih2x.h1 -> g2 [commit G2] | Wfc1x.h1 -> f1 | Whh1.h1 -> g1 (first touch: step t+1)
+//   (b) after h2(t):  Wfc1x.h2 -> f1 [commit F1] | Whh2.h2 -> g2 (first touch: step t+1)
+//   (c) after y1(t):  Wfc2x.y1 -> f2 [commit F2] | after cond(t+1): P1 -> g1, P3 -> f1 (first touch), P2 -> g2
+//   (d) after y2(t):  Wfc3.y2 -> f3 (first touch) [commit F3] | P4 -> f2 (first touch) [commit G1]
+// Tiles: T0 = [r | z] rows of the CTA's 64 units (128 rows), T1 = the n rows (64), F = 64 fc rows / classes.
+namespace {
+using wrnn_dense::Bundle;
+using wrnn_dense::Seg;
+typedef std::function<double(int rank, int m, int k)> DenseVal;
+struct DenseSeg {
+    int rows, nk, bsrc, dcol, first;
+    DenseVal val;
+    DenseSeg(int rows_, int nk_, int bsrc_, int dcol_, int first_, DenseVal val_) : rows(rows_), nk(nk_), bsrc(bsrc_), dcol(dcol_), first(first_), val(val_) {}
+};
+struct DenseBundle { int wait, commit; std::vector<DenseSeg> segs; };
+
+struct DensePack {
+    std::vector<Bundle> table;
+    std::vector<unsigned char> stream;     // [CL][stream_bytes]
+    std::vector<float> sv;                 // [CL][NSV][UPC]
+    unsigned stream_bytes = 0;
+};
+
+static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
+{
+    using namespace wrnn_dense;
+    const int R = DHID, F = 80, A = 32, KI = 1 + F + A, KC = F + A, RA = R + A;
+    std::vector<double> Wc((size_t)R * KC), w0(R), bI(R);
+    for (int j = 0; j < R; ++j) {
+        w0[j] = w->I_w[(size_t)j * KI];
+        bI[j] = w->I_b[j];
+        for (int k = 0; k < KC; ++k) Wc[(size_t)j * KC + k] = w->I_w[(size_t)j * KI + 1 + k];
+    }
+    std::vector<double> G1, G2, G3, u1, u2, u3, c1, c2, c3;
+    gemm_f64(w->r1_wih, R, 3 * R, R, Wc, KC, G1);
+    gemm_f64(w->r2_wih, RA, 3 * R, R, Wc, KC, G2);
+    gemm_f64(w->fc1_w, RA, R, R, Wc, KC, G3);
+    gemm_f64(w->r1_wih, R, 3 * R, R, w0, 1, u1);
+    gemm_f64(w->r2_wih, RA, 3 * R, R, w0, 1, u2);
+    gemm_f64(w->fc1_w, RA, R, R, w0, 1, u3);
+    gemm_f64(w->r1_wih, R, 3 * R, R, bI, 1, c1);
+    gemm_f64(w->r2_wih, RA, 3 * R, R, bI, 1, c2);
+    gemm_f64(w->fc1_w, RA, R, R, bI, 1, c3);
+
+    auto rowT0 = [](int rank, int m) { return m < UPC ? UPC * rank + m : R + UPC * rank + (m - UPC); };   // r rows, then z rows
+    auto rowN = [](int rank, int m) { return 2 * R + UPC * rank + m; };
+    auto unit = [](int rank, int m) { return UPC * rank + m; };
+    auto img = [](int i, int chunk) { return i * IMG_B + chunk * CHUNK_B; };
+    auto cnd = [](int chunk) { return 4 * IMG_B + chunk * CHUNK_B; };
+
+    std::vector<DenseBundle> prog;
+    // K = 512 products: T0 in four 128-wide bundles, 64-row tiles in two 256-wide bundles, interleaved so both advance
+    auto hidden = [&](int wait, int commit, int bimg, const float *W, int ld, int dT0, int dT1, int firstT0, int firstT1) {
+        for (int half = 0; half < 2; ++half) {
+            for (int kb = 2 * half; kb < 2 * half + 2; ++kb) {
+                DenseBundle b;
+                b.wait = kb == 0 ? wait : W_NONE;
+                b.commit = C_NONE;
+                b.segs.push_back(DenseSeg(128, 8, img(bimg, kb * 16), dT0, firstT0 && kb == 0, [=](int rank, int m, int k) { return (double)W[(size_t)rowT0(rank, m) * ld + kb * 128 + k]; }));
+                prog.push_back(b);
+            }
+            DenseBundle b;
+            b.wait = W_NONE;
+            b.commit = half == 1 ? commit : C_NONE;
+            b.segs.push_back(DenseSeg(UPC, 16, img(bimg, half * 32), dT1, firstT1 && half == 0, [=](int rank, int m, int k) { return (double)W[(size_t)rowN(rank, m) * ld + half * 256 + k]; }));
+            prog.push_back(b);
+        }
+    };
+    auto fc = [&](int wait, int commit, int bimg, const float *W, int ld, int dcol, int first, bool classes) {
+        for (int half = 0; half < 2; ++half) {
+            DenseBundle b;
+            b.wait = half == 0 ? wait : W_NONE;
+            b.commit = half == 1 ? commit : C_NONE;
+            b.segs.push_back(DenseSeg(UPC, 16, img(bimg, half * 32), dcol, first && half == 0, [=](int rank, int m, int k) { (void)classes; return (double)W[(size_t)unit(rank, m) * ld + half * 256 + k]; }));
+            prog.push_back(b);
+        }
+    };
+    // (a)
+    hidden(W_H1, C_G2, IMG_H1, w->r2_wih, RA, D_G2_T0, D_G2_1I, 0, 0);
+    fc(W_NONE, C_NONE, IMG_H1, w->fc1_w, RA, D_F1, 0, false);
+    hidden(W_NONE, C_NONE, IMG_H1, w->r1_whh, R, D_G1_T0, D_G1_1H, 1, 1);
+    // (b)
+    fc(W_H2, C_F1, IMG_H2, w->fc1_w, RA, D_F1, 0, false);
+    hidden(W_NONE, C_NONE, IMG_H2, w->r2_whh, R, D_G2_T0, D_G2_1H, 1, 1);
+    // (c)
+    fc(W_Y1, C_F2, IMG_Y1, w->fc2_w, RA, D_F2, 0, false);
+    {   // conditioning projections of step t+1; cond k: [0,80) mel | [80,112) a1 | [112,144) a2 | [144,176) a3 | [176,208) a4
+        const double *g1 = G1.data(), *g2 = G2.data(), *g3 = G3.data();
+        const float *r2 = w->r2_wih, *f1 = w->fc1_w, *f2 = w->fc2_w;
+        auto p2 = [=](int row, int k) { return k < KC ? g2[(size_t)row * KC + k] : (double)r2[(size_t)row * RA + R + (k - KC)]; };
+        DenseBundle c3;
+        c3.wait = W_COND;
+        c3.commit = C_NONE;
+        c3.segs.push_back(DenseSeg(128, 7, cnd(0), D_G1_T0, 0, [=](int rank, int m, int k) { return g1[(size_t)rowT0(rank, m) * KC + k]; }));
+        prog.push_back(c3);
+        DenseBundle c4;
+        c4.wait = W_NONE;
+        c4.commit = C_NONE;
+        c4.segs.push_back(DenseSeg(UPC, 7, cnd(0), D_G1_1I, 1, [=](int rank, int m, int k) { return g1[(size_t)rowN(rank, m) * KC + k]; }));
+        c4.segs.push_back(DenseSeg(UPC, 7, cnd(0), D_F1, 1, [=](int rank, int m, int k) { return g3[(size_t)unit(rank, m) * KC + k]; }));
+        c4.segs.push_back(DenseSeg(UPC, 2, cnd(18), D_F1, 0, [=](int rank, int m, int k) { return (double)f1[(size_t)unit(rank, m) * RA + R + k]; }));
+        prog.push_back(c4);
+        DenseBundle c5;
+        c5.wait = W_NONE;
+        c5.commit = C_NONE;
+        c5.segs.push_back(DenseSeg(128, 8, cnd(0), D_G2_T0, 0, [=](int rank, int m, int k) { return p2(rowT0(rank, m), k); }));
+        prog.push_back(c5);
+        DenseBundle c6;
+        c6.wait = W_NONE;
+        c6.commit = C_NONE;
+        c6.segs.push_back(DenseSeg(128, 1, cnd(16), D_G2_T0, 0, [=](int rank, int m, int k) { return p2(rowT0(rank, m), 128 + k); }));
+        c6.segs.push_back(DenseSeg(UPC, 9, cnd(0), D_G2_1I, 1, [=](int rank, int m, int k) { return p2(rowN(rank, m), k); }));
+        prog.push_back(c6);
+        // (d)
+        fc(W_Y2, C_F3, IMG_Y2, w->fc3_w, R, D_F3, 1, true);
+        DenseBundle d3;
+        d3.wait = W_NONE;
+        d3.commit = C_G1;
+        d3.segs.push_back(DenseSeg(UPC, 2, cnd(22), D_F2, 1, [=](int rank, int m, int k) { return (double)f2[(size_t)unit(rank, m) * RA + R + k]; }));
+        prog.push_back(d3);
+    }
+    if ((int)prog.size() > MAXBUNDLE) return fail(WRNN_ERR_INVALID, "dense program has %zu bundles (max %d)", prog.size(), MAXBUNDLE);
+
+    // serialise: table (identical for every rank) and the per-rank streams
+    out.table.assign(prog.size(), Bundle{});
+    unsigned off = 0;
+    for (size_t b = 0; b < prog.size(); ++b) {
+        Bundle &t = out.table[b];
+        t.src_off = off;
+        t.nseg = (uint16_t)prog[b].segs.size();
+        t.wait = (uint16_t)prog[b].wait;
+        t.commit = (uint16_t)prog[b].commit;
+        if (t.nseg > MAXSEG) return fail(WRNN_ERR_INVALID, "bundle %zu has %d segments", b, (int)t.nseg);
+        unsigned bytes = 0;
+        for (int s = 0; s < t.nseg; ++s) {
+            const DenseSeg &d = prog[b].segs[s];
+            t.seg[s] = Seg{(uint16_t)(bytes / 16), (uint16_t)d.rows, (uint16_t)d.nk, (uint16_t)(d.bsrc / 16), (uint16_t)d.dcol, (uint16_t)d.first};
+            bytes += (unsigned)d.rows * d.nk * 32;
+        }
+        if (bytes > (unsigned)SLOT) return fail(WRNN_ERR_INVALID, "bundle %zu is %u bytes (slot %d)", b, bytes, SLOT);
+        t.bytes = bytes;
+        off += bytes;
+    }
+    out.stream_bytes = off;
+    out.stream.assign((size_t)CL * off, 0);
+    for (int rank = 0; rank < CL; ++rank) {
+        unsigned short *dst = reinterpret_cast<unsigned short *>(out.stream.data() + (size_t)rank * off);
+        size_t e = 0;
+        for (size_t b = 0; b < prog.size(); ++b)
+            for (const DenseSeg &d : prog[b].segs)
+                for (int kc = 0; kc < 2 * d.nk; ++kc)             // image: [k chunk][row][8 k]
+                    for (int m = 0; m < d.rows; ++m)
+                        for (int i = 0; i < 8; ++i) dst[e++] = bf16_rne((float)d.val(rank, m, kc * 8 + i));
+    }
+    out.sv.assign((size_t)CL * NSV * UPC, 0.f);
+    for (int rank = 0; rank < CL; ++rank) {
+        float *sv = &out.sv[(size_t)rank * NSV * UPC];
+        for (int m = 0; m < UPC; ++m) {
+            const int ur = UPC * rank + m, rr = ur, rz = R + ur, rn = 2 * R + ur;
+            sv[DV_B1R * UPC + m] = (float)(c1[rr] + (double)w->r1_bih[rr] + (double)w->r1_bhh[rr]);
+            sv[DV_U1R * UPC + m] = (float)u1[rr];
+            sv[DV_B1Z * UPC + m] = (float)(c1[rz] + (double)w->r1_bih[rz] + (double)w->r1_bhh[rz]);
+            sv[DV_U1Z * UPC + m] = (float)u1[rz];
+            sv[DV_B1NI * UPC + m] = (float)(c1[rn] + (double)w->r1_bih[rn]);
+            sv[DV_U1N * UPC + m] = (float)u1[rn];
+            sv[DV_B1NH * UPC + m] = w->r1_bhh[rn];
+            sv[DV_B2R * UPC + m] = (float)(c2[rr] + (double)w->r2_bih[rr] + (double)w->r2_bhh[rr]);
+            sv[DV_U2R * UPC + m] = (float)u2[rr];
+            sv[DV_B2Z * UPC + m] = (float)(c2[rz] + (double)w->r2_bih[rz] + (double)w->r2_bhh[rz]);
+            sv[DV_U2Z * UPC + m] = (float)u2[rz];
+            sv[DV_B2NI * UPC + m] = (float)(c2[rn] + (double)w->r2_bih[rn]);
+            sv[DV_U2N * UPC + m] = (float)u2[rn];
+            sv[DV_B2NH * UPC + m] = w->r2_bhh[rn];
+            sv[DV_B3 * UPC + m] = (float)(c3[ur] + (double)w->fc1_b[ur]);
+            sv[DV_U3 * UPC + m] = (float)u3[ur];
+            sv[DV_B4 * UPC + m] = w->fc2_b[ur];
+            sv[DV_B5 * UPC + m] = w->fc3_b[ur];
+        }
+    }
+    return WRNN_OK;
+}
+}   // namespace
+
+extern "C" int32_t wrnn_dense_layout(const wrnn_config *cfg, int64_t *layout)
+{
+    if (!cfg || !layout) return fail(WRNN_ERR_INVALID, "null argument");
+    int rows5, nprod5, n_u;
+    wrnn_config c = *cfg;
+    c.precision = WRNN_PREC_BF16_DENSE;
+    int32_t rc = derive_layout(c, rows5, nprod5, n_u);
+    if (rc) return rc;
+    // the program does not depend on the weight values: pack zeros to measure it
+    std::vector<float> z((size_t)1536 * 544, 0.f);
+    wrnn_weights w = {z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data()};
+    DensePack dp;
+    rc = pack_dense(&w, dp);
+    if (rc) return rc;
+    const int64_t v[8] = {(int64_t)dp.table.size(), dp.stream_bytes, (int64_t)sizeof(Bundle), wrnn_dense::CL, wrnn_dense::UPC, wrnn_dense::BC, wrnn_dense::NSV, 0};
+    memcpy(layout, v, sizeof v);
+    return WRNN_OK;
+}
+
+extern "C" int32_t wrnn_dense_pack_host(const wrnn_config *cfg, const wrnn_weights *w, uint8_t *stream, uint8_t *table, float *sv)
+{
+    if (!cfg || !w || !stream || !table || !sv) return fail(WRNN_ERR_INVALID, "null argument");
+    int rows5, nprod5, n_u;
+    wrnn_config c = *cfg;
+    c.precision = WRNN_PREC_BF16_DENSE;
+    int32_t rc = derive_layout(c, rows5, nprod5, n_u);
+    if (rc) return rc;
+    DensePack dp;
+    rc = pack_dense(w, dp);
+    if (rc) return rc;
+    memcpy(stream, dp.stream.data(), dp.stream.size());
+    memcpy(table, dp.table.data(), dp.table.size() * sizeof(Bundle));
+    memcpy(sv, dp.sv.data(), dp.sv.size() * sizeof(float));
+    return WRNN_OK;
+}
+
 extern "C" int64_t wrnn_packed_floats(const wrnn_config *cfg)
 {
     int rows5, nprod5, n_u;
@@ -371,6 +624,27 @@ extern "C" int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w)
     for (int i = 0; i < 16; ++i)
         if (!pp[i]) return fail(WRNN_ERR_INVALID, "weight pointer %d is null", i);
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->dense) {
+        DensePack dp;
+        int32_t rc = pack_dense(w, dp);
+        if (rc) return rc;
+        cudaFree(h->dense_stream);
+        cudaFree(h->dense_table);
+        cudaFree(h->dense_sv);
+        h->dense_stream = nullptr;
+        h->dense_table = nullptr;
+        h->dense_sv = nullptr;
+        CUDA_TRY(cudaMalloc(&h->dense_stream, dp.stream.size()));
+        CUDA_TRY(cudaMalloc(&h->dense_table, dp.table.size() * sizeof(wrnn_dense::Bundle)));
+        CUDA_TRY(cudaMalloc(&h->dense_sv, dp.sv.size() * sizeof(float)));
+        CUDA_TRY(cudaMemcpy(h->dense_stream, dp.stream.data(), dp.stream.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->dense_table, dp.table.data(), dp.table.size() * sizeof(wrnn_dense::Bundle), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(h->dense_sv, dp.sv.data(), dp.sv.size() * sizeof(float), cudaMemcpyHostToDevice));
+        h->dense_nb = (int)dp.table.size();
+        h->dense_stream_bytes = dp.stream_bytes;
+        h->loaded = true;
+        return WRNN_OK;
+    }
     std::vector<float> img32, img;
     pack_images(h->cfg.n_classes, h->rows5, w, img32);
     finish_images(h->rows5, h->bf16w, img32, img);
@@ -473,6 +747,57 @@ extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const 
     CUDA_TRY(cudaMemcpyAsync(h->fold_dev + h->fold_cap, fold_limit, (size_t)num_folds * sizeof(long long), cudaMemcpyHostToDevice, st));
 
     h->last_ms = 0.f;
+    if (h->dense) {
+        // every launch keeps as many clusters busy as fit at once; folds are dealt evenly, at most BC per cluster
+        using namespace wrnn_dense;
+        if (cond_rows > 0x7fffffffll) return fail(WRNN_ERR_INVALID, "dense path indexes conditioning rows with 32 bits (got %lld rows)", (long long)cond_rows);
+        const int cap = h->dense_clusters * BC;
+        for (int b0 = 0; b0 < num_folds; b0 += cap) {
+            const int nb = num_folds - b0 < cap ? num_folds - b0 : cap;
+            int ncl = (nb + BC - 1) / BC;
+            const char *spread = getenv("WRNN_DENSE_SPREAD");      // development knob: use every cluster even for few folds
+            if (spread && atoi(spread) > 0) ncl = nb < h->dense_clusters ? nb : h->dense_clusters;
+            DParams dp;
+            memset(&dp, 0, sizeof dp);
+            dp.wstream = h->dense_stream;
+            dp.table = h->dense_table;
+            dp.sv = h->dense_sv;
+            dp.mels = mels;
+            dp.aux = aux;
+            dp.fold_start = h->fold_dev;
+            dp.fold_limit = h->fold_dev + h->fold_cap;
+            dp.uniforms = uniforms;
+            dp.forced_x = forced_x;
+            dp.logits_out = logits_out;
+            dp.samples_out = samples_out;
+            dp.labels_out = labels_out;
+            dp.seed = seed;
+            dp.status = h->status;
+            dp.stream_bytes = h->dense_stream_bytes;
+            dp.nb = h->dense_nb;
+            dp.B = num_folds;
+            dp.S = steps;
+            dp.fold0 = b0;
+            dp.nfolds = nb;
+            dp.per = (nb + ncl - 1) / ncl;
+            CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
+            CUDA_TRY(cudaEventRecord(h->ev0, st));
+            wavernn_dense_kernel<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaEventRecord(h->ev1, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            h->last_ms += ms;
+            h->launches += 1;
+            h->smem_bytes = SM_TOTAL;
+            int status[4];
+            CUDA_TRY(cudaMemcpy(status, h->status, sizeof status, cudaMemcpyDeviceToHost));
+            h->last_status = status[0];
+            if (status[0] != 0) return fail(WRNN_ERR_TIMEOUT, "dense kernel watchdog fired (wait code %d): a pipeline barrier never completed", status[0]);
+        }
+        return WRNN_OK;
+    }
     const int max_chunk = MAXG * BT;
     for (int b0 = 0; b0 < num_folds; b0 += max_chunk) {
         const int nb = num_folds - b0 < max_chunk ? num_folds - b0 : max_chunk;
@@ -545,12 +870,12 @@ extern "C" int32_t wrnn_get_stage_cycles(wrnn_handle *h, int64_t *out, int32_t n
 extern "C" int32_t wrnn_get_info(wrnn_handle *h, wrnn_info *out)
 {
     if (!h || !out) return fail(WRNN_ERR_INVALID, "null argument");
-    out->ctas = NCTA;
-    out->threads = NTHREADS;
-    out->smem_bytes = h->smem_bytes;
-    out->folds_per_group = BT;
-    out->max_folds_per_launch = MAXG * BT;
-    out->exchanges_per_step = NEXCH;
+    out->ctas = h->dense ? h->dense_clusters * wrnn_dense::CL : NCTA;
+    out->threads = h->dense ? wrnn_dense::DTHREADS : NTHREADS;
+    out->smem_bytes = h->dense ? wrnn_dense::SM_TOTAL : h->smem_bytes;
+    out->folds_per_group = h->dense ? wrnn_dense::BC : BT;
+    out->max_folds_per_launch = h->dense ? h->dense_clusters * wrnn_dense::BC : MAXG * BT;
+    out->exchanges_per_step = h->dense ? 6 : NEXCH;
     out->sm_count = h->sm_count;
     out->launches = h->launches;
     out->epilogue_launches = g_epilogue_launches;

@@ -1,0 +1,581 @@
+// wavernn_dense.cuh -- dense-regime step loop of WaveRNN.generate (fatchord_version.py:171-222) on the Blackwell
+// tensor cores: tcgen05.mma (bf16 x bf16 -> fp32 in tensor memory) with the weights STREAMED from L2 by bulk-TMA and
+// the folds of a cluster advanced together.  precision = WRNN_PREC_BF16_DENSE.
+//
+// Work split.  A thread-block cluster of CL = 8 CTAs owns up to BC = 32 folds for all their steps; there is no
+// grid-level synchronisation (clusters are independent, so a launch may hold more clusters than fit at once).
+// CTA `rank` of a cluster owns hidden units [64 rank, 64 rank + 64) of rnn1, rnn2, fc1, fc2 and classes
+// [64 rank, +64) of fc3.  Per step it multiplies its weight rows (MMA operand A, M = 128 rows, K-major, no swizzle)
+// with the activations of ALL 512 units of the cluster's folds (operand B, N = 32 folds, K-major), which every CTA
+// keeps as bf16 images in shared memory:  image byte (k, f) = (k / 8) * 512 + f * 16 + (k % 8) * 2.
+// A CTA's freshly computed 64 units are a contiguous 4 KB block of such an image; it is written locally and
+// broadcast to the 7 peers with cp.async.bulk shared::cta -> shared::cluster, completing on the peers' mbarriers.
+//
+// Algebra (same folding as the fp32 kernel, csrc/wavernn_b200.cu::pack_images): the input layer I is folded into
+// rnn1 / rnn2 / fc1, the sample x enters only through fp32 rank-1 terms in the epilogues, and everything that does
+// not depend on the value produced by the current stage is issued early ("deferred" segments), so the per-step
+// dependent chain is  E1 -> Wih2x.h1 -> E2 -> Wfc1x.h2 -> E3 -> Wfc2x.y1 -> E4 -> Wfc3.y2 -> E5 -> sample.
+//
+// Warp roles (352 threads): warps 0-7 epilogue (tensor memory -> registers -> gates / relu / sampling), warp 8 lane 0
+// issues every tcgen05.mma, warps 9 and 10 lane 0 stream the weight bundles (one ring slot each).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wrnn_dense {
+
+constexpr int CL = 8;                         // CTAs per cluster
+constexpr int DHID = 512;
+constexpr int UPC = DHID / CL;                 // hidden units (and RAW classes) per CTA
+constexpr int BC = 32;                        // folds per cluster = MMA N
+constexpr int NEPI = 256;                     // epilogue threads
+constexpr int MMA_WARP = 8, PROD_WARP0 = 9;
+constexpr int DTHREADS = NEPI + 96;
+constexpr int SLOT = 32768, NSLOT = 2;        // weight ring
+constexpr int CHUNK_B = BC * 16;              // one k-chunk (8 k) of an activation image
+constexpr int IMG_B = (DHID / 8) * CHUNK_B;    // 32 KB: one activation image
+constexpr int COND_CHUNKS = 26;               // 208 conditioning inputs: mel 80 | a1 | a2 | a3 | a4
+constexpr int COND_B = COND_CHUNKS * CHUNK_B;
+constexpr int SLICE_B = (UPC / 8) * CHUNK_B;  // a CTA's 64 units of an image
+constexpr int NCLASS = 512;                   // RAW 9 bit
+constexpr int FPC = BC / CL;                  // folds sampled by each CTA
+constexpr int MAXSEG = 4, MAXBUNDLE = 40;
+constexpr int NSV = 18;                       // per-row fp32 vectors (biases, x coefficients), [NSV][UPC] per CTA
+
+enum { IMG_H1 = 0, IMG_H2 = 1, IMG_Y1 = 2, IMG_Y2 = 3 };
+enum { W_NONE = 0, W_H1 = 1, W_H2 = 2, W_Y1 = 3, W_Y2 = 4, W_COND = 5 };       // wait before a bundle
+enum { C_NONE = 0, C_G2 = 1, C_F1 = 2, C_F2 = 3, C_F3 = 4, C_G1 = 5 };         // commit after a bundle
+// tensor-memory columns of the fp32 accumulators (BC columns each)
+enum { D_G1_T0 = 0, D_G1_1H = 32, D_G1_1I = 64, D_G2_T0 = 96, D_G2_1H = 128, D_G2_1I = 160, D_F1 = 192, D_F2 = 224, D_F3 = 256 };
+enum { DV_B1R = 0, DV_U1R, DV_B1Z, DV_U1Z, DV_B1NI, DV_U1N, DV_B1NH, DV_B2R, DV_U2R, DV_B2Z, DV_U2Z, DV_B2NI, DV_U2N, DV_B2NH, DV_B3, DV_U3, DV_B4, DV_B5 };
+
+struct Seg {
+    uint16_t off16;    // byte offset of the A tile in the ring slot / 16
+    uint16_t rows;     // valid rows of the A tile (64 or 128); rows beyond alias the following bytes and feed unused lanes
+    uint16_t nk;       // k-steps of 16
+    uint16_t bsrc16;   // B operand: byte offset from the first activation image / 16
+    uint16_t dcol;     // accumulator column
+    uint16_t first;    // 1: the first k-step overwrites the accumulator
+};
+struct Bundle {
+    uint32_t bytes, src_off;     // payload size and offset in the per-rank stream
+    uint16_t nseg, wait, commit, pad;
+    Seg seg[MAXSEG];
+};
+
+// shared-memory map (bytes)
+constexpr int SM_RING = 0;
+constexpr int SM_IMG = SM_RING + NSLOT * SLOT;                 // 4 activation images, then the conditioning image
+constexpr int SM_COND = SM_IMG + 4 * IMG_B;
+constexpr int SM_SCRATCH = SM_COND + COND_B;                   // [BC][UPC] fp32: candidate state n (E1/E2), logits staging (E5)
+constexpr int SM_SAMP = SM_SCRATCH + BC * UPC * 4;             // [CL src][FPC][UPC] fp32 logits of this CTA's folds
+constexpr int SM_X = SM_SAMP + CL * FPC * UPC * 4;             // [BC] fp32 fed-back sample
+constexpr int SM_FOLD = SM_X + BC * 4;                         // [2][BC] int32 first row / limit row
+constexpr int SM_TAB = SM_FOLD + 2 * BC * 4;
+constexpr int SM_BAR = SM_TAB + MAXBUNDLE * (int)sizeof(Bundle);
+enum { B_FULL = 0, B_EMPTY = 2, B_ACT = 4, B_LG = 8, B_X = 9, B_COND = 10, B_ACC = 11, B_DONE = 16, NBAR = 17 };
+constexpr int SM_TMEM = SM_BAR + NBAR * 8;
+constexpr int SM_TOTAL = SM_TMEM + 16;
+
+struct DParams {
+    const uint8_t *wstream;        // [CL][stream_bytes] bf16 operand tiles in bundle order
+    const Bundle *table;           // [nb]
+    const float *sv;               // [CL][NSV][UPC]
+    const float *mels, *aux;       // fp32 [rows][80], [rows][128]  (UpsampleNetwork output, unfolded)
+    const long long *fold_start, *fold_limit;
+    const float *uniforms, *forced_x;
+    float *logits_out, *samples_out;
+    int *labels_out;
+    unsigned long long seed;
+    int *status;
+    uint32_t stream_bytes;
+    int nb;                        // bundles per step
+    int B, S;                      // folds of the whole call (row stride of uniforms / logits), steps
+    int fold0, nfolds, per;        // this launch: folds [fold0, fold0 + nfolds), `per` per cluster
+};
+
+// ---- PTX helpers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) { uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r; }
+__device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) { asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory"); }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// capped wait (~1 s): a stuck pipeline sets *status and lets every role run out instead of hanging the GPU
+__device__ __noinline__ bool mbar_wait_slow(uint32_t bar, unsigned parity, int *status, int code)
+{
+    const long long t0 = clock64();
+    for (;;) {
+        for (int i = 0; i < 256; ++i)
+            if (mbar_try(bar, parity)) return true;
+        if (clock64() - t0 > 2000000000ll) {
+            atomicCAS(status, 0, code);
+            return false;
+        }
+    }
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, unsigned parity, int *status, int code)
+{
+    if (mbar_try(bar, parity)) return true;
+    return mbar_wait_slow(bar, parity, status, code);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, unsigned bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, uint32_t src_cta, unsigned bytes, uint32_t bar_cluster)
+{
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]),
+                   "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B stored contiguously (128 B),
+// LBO = byte distance between the two core matrices of a k-step along K, SBO = between 8-row groups (128 B here)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes)
+{
+    const uint32_t lo = ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+    const uint32_t hi = (128u >> 4) | (1u << 14);            // SBO | descriptor version 1 (Blackwell)
+    return ((uint64_t)hi << 32) | lo;
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BC
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+__device__ __forceinline__ float sigmoid_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanh_(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
+{
+    const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&b);
+}
+
+// Philox4x32-10, same stream as the fp32 kernel: uniform j of (step, fold) = word j & 3 of Philox({step, fold, j >> 2, 0}, seed)
+__device__ __forceinline__ float philox_u01(unsigned long long seed, int step, int fold)
+{
+    uint4 c = make_uint4((unsigned)step, (unsigned)fold, 0u, 0u);
+    uint2 k = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+#pragma unroll 1
+    for (int i = 0; i < 10; ++i) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return (float)(c.x >> 8) * (1.0f / 16777216.0f);
+}
+
+// ---- conditioning: item (kc, f) = 8 consecutive conditioning inputs of fold f, fp32 in global, bf16 in the image ----
+struct CondRegs { float4 v[4][2]; };
+__device__ __forceinline__ void cond_load(const DParams &p, const int *fold_row0, const int *fold_lim, int nf, int tid, int step, CondRegs &cr)
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = tid + NEPI * j;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (i < COND_CHUNKS * BC) {
+            const int f = i & (BC - 1), kc = i >> 5;
+            const long long row = (long long)fold_row0[f] + step;
+            if (f < nf && step < p.S && row < (long long)fold_lim[f]) {
+                const float *src = kc < 10 ? p.mels + row * 80 + kc * 8 : p.aux + row * 128 + (kc - 10) * 8;
+                a = __ldg(reinterpret_cast<const float4 *>(src));
+                b = __ldg(reinterpret_cast<const float4 *>(src) + 1);
+            }
+        }
+        cr.v[j][0] = a;
+        cr.v[j][1] = b;
+    }
+}
+__device__ __forceinline__ void cond_store(uint8_t *cond_img, int tid, const CondRegs &cr)
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = tid + NEPI * j;
+        if (i < COND_CHUNKS * BC) {
+            const int f = i & (BC - 1), kc = i >> 5;
+            const float4 a = cr.v[j][0], b = cr.v[j][1];
+            *reinterpret_cast<uint4 *>(cond_img + kc * CHUNK_B + f * 16) = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+        }
+    }
+}
+
+// broadcast this CTA's 4 KB slice of activation image `img` to the 7 peers (one thread)
+__device__ __forceinline__ void send_slice(uint32_t smem_base, int img, uint32_t rank)
+{
+    const uint32_t src = smem_base + SM_IMG + img * IMG_B + rank * SLICE_B;
+    const uint32_t bar = smem_base + SM_BAR + (B_ACT + img) * 8;
+    mbar_expect_tx(bar, (CL - 1) * SLICE_B);
+#pragma unroll 1
+    for (uint32_t q = 1; q < CL; ++q) {
+        const uint32_t peer = (rank + q) & (CL - 1);
+        bulk_s2peer(mapa(src, peer), src, SLICE_B, mapa(bar, peer));
+    }
+}
+
+// GRU epilogue of one layer (torch.nn.GRUCell, fatchord_version.py:190,194): lanes 0-63 of the accumulators hold
+// r (tile 0), W_hn.h (tile 1h) and W_in.x (tile 1i) of the CTA's units, lanes 64-127 of tile 0 hold z.
+// R threads (quads 0,1) publish n = tanh(i_n + r * h_n) through shared memory; Z threads (quads 2,3) own the fp32
+// state, finish h' = n + z (h - n) and write its bf16 image.
+__device__ __forceinline__ void gru_epilogue(uint32_t tmem, int col_t0, int col_1h, int col_1i, uint8_t *smem, int img, uint32_t rank, int warp, int lane,
+                                             float b_r, float u_r, float b_ni, float u_n, float b_nh, float b_z, float u_z, float (&hprev)[16])
+{
+    const int q = warp & 3, hf = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float *xs = reinterpret_cast<const float *>(smem + SM_X);
+    float *scratch = reinterpret_cast<float *>(smem + SM_SCRATCH);
+    float zz[16];
+    if (q < 2) {
+        const int u = q * 32 + lane;
+        float r[16], nh[16], ni[16];
+        tc_ld16(tmem + lane_base + col_t0 + 16 * hf, r);
+        tc_ld16(tmem + lane_base + col_1h + 16 * hf, nh);
+        tc_ld16(tmem + lane_base + col_1i + 16 * hf, ni);
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int f = 16 * hf + j;
+            const float x = xs[f];
+            const float rr = sigmoid_(r[j] + fmaf(x, u_r, b_r));
+            const float nn = tanh_(ni[j] + fmaf(x, u_n, b_ni) + rr * (nh[j] + b_nh));
+            scratch[f * UPC + u] = nn;
+        }
+    } else {
+        float z[16];
+        tc_ld16(tmem + lane_base + col_t0 + 16 * hf, z);
+        tc_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) zz[j] = sigmoid_(z[j] + fmaf(xs[16 * hf + j], u_z, b_z));
+    }
+    tc_fence_before();
+    epi_sync();
+    if (q >= 2) {
+        const int u = (q - 2) * 32 + lane;
+        uint8_t *dst = smem + SM_IMG + img * IMG_B + (rank * (UPC / 8) + (u >> 3)) * CHUNK_B + (u & 7) * 2;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int f = 16 * hf + j;
+            const float nn = scratch[f * UPC + u];
+            const float h = fmaf(zz[j], hprev[j] - nn, nn);
+            hprev[j] = h;
+            *reinterpret_cast<__nv_bfloat16 *>(dst + f * 16) = __float2bfloat16_rn(h);
+        }
+        fence_async_smem();
+    }
+    epi_sync();
+}
+
+// fc epilogue: rows 0-63 (quads 0,1) hold the CTA's units; relu(acc + b + x u) -> bf16 image
+__device__ __forceinline__ void fc_epilogue(uint32_t tmem, int col, uint8_t *smem, int img, uint32_t rank, int warp, int lane, float b, float ux)
+{
+    const int q = warp & 3, hf = warp >> 2;
+    if (q < 2) {
+        const int u = q * 32 + lane;
+        const float *xs = reinterpret_cast<const float *>(smem + SM_X);
+        float a[16];
+        tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + col + 16 * hf, a);
+        tc_ld_wait();
+        uint8_t *dst = smem + SM_IMG + img * IMG_B + (rank * (UPC / 8) + (u >> 3)) * CHUNK_B + (u & 7) * 2;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int f = 16 * hf + j;
+            const float y = fmaxf(a[j] + fmaf(xs[f], ux, b), 0.0f);
+            *reinterpret_cast<__nv_bfloat16 *>(dst + f * 16) = __float2bfloat16_rn(y);
+        }
+        fence_async_smem();
+    }
+    tc_fence_before();
+    epi_sync();
+}
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavernn_dense_kernel(const DParams p)
+{
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int ci = blockIdx.x / CL;
+    const int cfold0 = p.fold0 + ci * p.per;
+    int nf = p.fold0 + p.nfolds - cfold0;
+    nf = nf < p.per ? nf : p.per;
+    if (nf <= 0) return;                                       // whole cluster: nothing to do
+    const uint32_t sb = s32(smem);
+    const uint32_t bar0 = sb + SM_BAR;
+    int *fold_row0 = reinterpret_cast<int *>(smem + SM_FOLD), *fold_lim = fold_row0 + BC;
+    Bundle *tab = reinterpret_cast<Bundle *>(smem + SM_TAB);
+
+    // ---- set-up: zero the images / conditioning / x, barriers, bundle table, tensor memory
+    for (int i = tid; i < (SM_FOLD - SM_IMG) / 16; i += DTHREADS) reinterpret_cast<uint4 *>(smem + SM_IMG)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < p.nb * (int)(sizeof(Bundle) / 4); i += DTHREADS) reinterpret_cast<uint32_t *>(tab)[i] = reinterpret_cast<const uint32_t *>(p.table)[i];
+    if (tid < BC) {
+        const int f = tid;
+        fold_row0[f] = f < nf ? (int)p.fold_start[cfold0 + f] : 0;
+        fold_lim[f] = f < nf ? (int)p.fold_limit[cfold0 + f] : 0;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < NSLOT; ++s) {
+            mbar_init(bar0 + (B_FULL + s) * 8, 1);
+            mbar_init(bar0 + (B_EMPTY + s) * 8, 1);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(bar0 + (B_ACT + i) * 8, 1);
+        mbar_init(bar0 + B_LG * 8, 1);
+        mbar_init(bar0 + B_X * 8, CL * FPC);
+        mbar_init(bar0 + B_COND * 8, NEPI / 32);
+        for (int i = 0; i < 5; ++i) mbar_init(bar0 + (B_ACC + i) * 8, 1);
+        mbar_init(bar0 + B_DONE * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sb + SM_TMEM), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<const uint32_t *>(smem + SM_TMEM);
+    const int S = p.S;
+
+    if (warp >= PROD_WARP0) {
+        // ===== weight stream: producer pw owns ring slot pw; bundle gb of the launch goes to slot gb & 1 =====
+        if (lane == 0) {
+            const int pw = warp - PROD_WARP0;
+            const uint8_t *src = p.wstream + (size_t)rank * p.stream_bytes;
+            const uint32_t full = bar0 + (B_FULL + pw) * 8, empty = bar0 + (B_EMPTY + pw) * 8, dst = sb + SM_RING + pw * SLOT;
+            const long long total = (long long)(S + 1) * p.nb;
+            int b = pw;                                         // bundle index within the step
+            for (long long gb = pw, use = 0; gb < total; gb += NSLOT, ++use) {
+                if (use > 0 && !mbar_wait(empty, (unsigned)((use - 1) & 1), p.status, 1)) break;
+                const uint32_t bytes = tab[b].bytes;
+                mbar_expect_tx(full, bytes);
+                bulk_g2s(dst, src + tab[b].src_off, bytes, full);
+                b += NSLOT;
+                if (b >= p.nb) b -= p.nb;
+            }
+        }
+    } else if (warp == MMA_WARP) {
+        // ===== MMA issue: one thread walks the bundle table once per step; t = -1 primes the accumulators of step 0
+        if (lane == 0) {
+            unsigned ph_full = 0, ph_wait = 0;                  // phase bits: ring slots / wait events
+            long long gb = 0;
+            bool ok = true;
+            for (int t = -1; t < S && ok; ++t) {
+                const bool pre = t < 0;
+                for (int b = 0; b < p.nb && ok; ++b, ++gb) {
+                    const Bundle &bd = tab[b];
+                    const int w = bd.wait;
+                    if (w != W_NONE && (w == W_COND || !pre)) {
+                        const uint32_t wb = w == W_COND ? bar0 + B_COND * 8 : bar0 + (B_ACT + (w - W_H1)) * 8;
+                        ok = mbar_wait(wb, (ph_wait >> w) & 1u, p.status, 10 + w);
+                        ph_wait ^= 1u << w;
+                        if (!ok) break;
+                    }
+                    const int slot = (int)(gb & 1);
+                    ok = mbar_wait(bar0 + (B_FULL + slot) * 8, (ph_full >> slot) & 1u, p.status, 2);
+                    ph_full ^= 1u << slot;
+                    if (!ok) break;
+                    tc_fence_after();
+                    const uint32_t slot_base = sb + SM_RING + slot * SLOT;
+                    for (int s = 0; s < bd.nseg; ++s) {
+                        const Seg sg = bd.seg[s];
+                        const uint32_t a0 = slot_base + (uint32_t)sg.off16 * 16, b0 = sb + SM_IMG + (uint32_t)sg.bsrc16 * 16;
+                        const uint32_t lbo_a = (uint32_t)sg.rows * 16, step_a = (uint32_t)sg.rows * 32;
+                        for (int k = 0; k < sg.nk; ++k)
+                            tc_mma(tmem + sg.dcol, smem_desc(a0 + k * step_a, lbo_a), smem_desc(b0 + k * 2 * CHUNK_B, CHUNK_B), IDESC, (k > 0 || !sg.first) ? 1u : 0u);
+                    }
+                    tc_commit(bar0 + (B_EMPTY + slot) * 8);
+                    const int c = bd.commit;
+                    if (c != C_NONE && (c == C_G1 || !pre)) tc_commit(bar0 + (B_ACC + (c == C_G1 ? 0 : c)) * 8);
+                }
+            }
+            tc_commit(bar0 + B_DONE * 8);
+            mbar_wait(bar0 + B_DONE * 8, 0, p.status, 3);
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int q = warp & 3;
+        const float *sv = p.sv + (size_t)rank * NSV * UPC;
+        const int u = (q & 1) * 32 + lane;                      // unit of this thread's accumulator lane (R: q 0,1; Z: q 2,3)
+        const float b1r = sv[DV_B1R * UPC + u], u1r = sv[DV_U1R * UPC + u], b1z = sv[DV_B1Z * UPC + u], u1z = sv[DV_U1Z * UPC + u];
+        const float b1ni = sv[DV_B1NI * UPC + u], u1n = sv[DV_U1N * UPC + u], b1nh = sv[DV_B1NH * UPC + u];
+        const float b2r = sv[DV_B2R * UPC + u], u2r = sv[DV_U2R * UPC + u], b2z = sv[DV_B2Z * UPC + u], u2z = sv[DV_U2Z * UPC + u];
+        const float b2ni = sv[DV_B2NI * UPC + u], u2n = sv[DV_U2N * UPC + u], b2nh = sv[DV_B2NH * UPC + u];
+        const float b3 = sv[DV_B3 * UPC + u], u3 = sv[DV_U3 * UPC + u], b4 = sv[DV_B4 * UPC + u], b5 = sv[DV_B5 * UPC + u];
+        float h1[16], h2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) h1[j] = h2[j] = 0.f;
+        uint8_t *cond_img = smem + SM_COND;
+        CondRegs cr;
+        // prologue: conditioning of step 0 -> image, conditioning of step 1 -> registers
+        cond_load(p, fold_row0, fold_lim, nf, tid, 0, cr);
+        cond_store(cond_img, tid, cr);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + B_COND * 8);
+        cond_load(p, fold_row0, fold_lim, nf, tid, 1, cr);
+
+        unsigned ph = 0;                                        // phase bits of B_ACC + {0..4}, B_X (bit 5), B_LG (bit 6)
+        bool ok = true;
+        for (int t = 0; t < S && ok; ++t) {
+            // ---- E1: h1(t) = GRU1(I(x(t-1), c(t)), h1(t-1)) -- fatchord_version.py:188-190
+            ok = mbar_wait(bar0 + (B_ACC + 0) * 8, ph & 1u, p.status, 20);
+            ph ^= 1u;
+            if (!ok) break;
+            if (t > 0) {
+                ok = mbar_wait(bar0 + B_X * 8, (ph >> 5) & 1u, p.status, 25);
+                ph ^= 1u << 5;
+                if (!ok) break;
+            }
+            tc_fence_after();
+            gru_epilogue(tmem, D_G1_T0, D_G1_1H, D_G1_1I, smem, IMG_H1, rank, warp, lane, b1r, u1r, b1ni, u1n, b1nh, b1z, u1z, h1);
+            if (tid == 0) send_slice(sb, IMG_H1, rank);
+            // conditioning of step t+1 -> image (all MMAs that read the image of step t completed before the G1 commit)
+            cond_store(cond_img, tid, cr);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + B_COND * 8);
+            cond_load(p, fold_row0, fold_lim, nf, tid, t + 2, cr);
+            // ---- E2: h2(t) = GRU2([x + h1, a2], h2(t-1)) -- :192-194
+            ok = mbar_wait(bar0 + (B_ACC + C_G2) * 8, (ph >> C_G2) & 1u, p.status, 21);
+            ph ^= 1u << C_G2;
+            if (!ok) break;
+            tc_fence_after();
+            gru_epilogue(tmem, D_G2_T0, D_G2_1H, D_G2_1I, smem, IMG_H2, rank, warp, lane, b2r, u2r, b2ni, u2n, b2nh, b2z, u2z, h2);
+            if (tid == 0) send_slice(sb, IMG_H2, rank);
+            // ---- E3: y1 = relu(fc1([x + h1 + h2, a3])) -- :196-198
+            ok = mbar_wait(bar0 + (B_ACC + C_F1) * 8, (ph >> C_F1) & 1u, p.status, 22);
+            ph ^= 1u << C_F1;
+            if (!ok) break;
+            tc_fence_after();
+            fc_epilogue(tmem, D_F1, smem, IMG_Y1, rank, warp, lane, b3, u3);
+            if (tid == 0) send_slice(sb, IMG_Y1, rank);
+            // ---- E4: y2 = relu(fc2([y1, a4])) -- :200-201
+            ok = mbar_wait(bar0 + (B_ACC + C_F2) * 8, (ph >> C_F2) & 1u, p.status, 23);
+            ph ^= 1u << C_F2;
+            if (!ok) break;
+            tc_fence_after();
+            fc_epilogue(tmem, D_F2, smem, IMG_Y2, rank, warp, lane, b4, 0.0f);
+            if (tid == 0) send_slice(sb, IMG_Y2, rank);
+            // ---- E5: logits = fc3(y2) (:202): this CTA's 64 classes of every fold -> the CTA that samples the fold
+            ok = mbar_wait(bar0 + (B_ACC + C_F3) * 8, (ph >> C_F3) & 1u, p.status, 24);
+            ph ^= 1u << C_F3;
+            if (!ok) break;
+            tc_fence_after();
+            if (q < 2) {
+                const int hf = warp >> 2;
+                float a[16];
+                tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + D_F3 + 16 * hf, a);
+                tc_ld_wait();
+                float *stage = reinterpret_cast<float *>(smem + SM_SCRATCH);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) stage[(16 * hf + j) * UPC + u] = a[j] + b5;
+                fence_async_smem();
+            }
+            tc_fence_before();
+            epi_sync();
+            if (tid == 0) {
+                const uint32_t lgbar = bar0 + B_LG * 8;
+                mbar_expect_tx(lgbar, CL * FPC * UPC * 4);
+#pragma unroll 1
+                for (uint32_t d = 0; d < CL; ++d)               // folds FPC d .. FPC d + FPC - 1 are sampled by CTA d
+                    bulk_s2peer(mapa(sb + SM_SAMP + rank * (FPC * UPC * 4), d), sb + SM_SCRATCH + d * (FPC * UPC * 4), FPC * UPC * 4, mapa(lgbar, d));
+            }
+            // ---- sampling (:210-216): warp w < FPC takes fold FPC rank + w; softmax + inverse CDF as in the fp32 kernel
+            if (warp < FPC) {
+                ok = mbar_wait(bar0 + B_LG * 8, (ph >> 6) & 1u, p.status, 26);
+                ph ^= 1u << 6;
+                if (!ok) break;
+                const int fl = FPC * (int)rank + warp;          // fold within the cluster
+                const int bglob = cfold0 + fl;
+                const float *lg = reinterpret_cast<const float *>(smem + SM_SAMP) + ((lane >> 2) * FPC + warp) * UPC + (lane & 3) * 16;
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    const float4 qv = *reinterpret_cast<const float4 *>(lg + j);
+                    v[j] = qv.x; v[j + 1] = qv.y; v[j + 2] = qv.z; v[j + 3] = qv.w;
+                }
+                if (p.logits_out && fl < nf) {
+                    float *dst = p.logits_out + ((size_t)t * p.B + bglob) * NCLASS + lane * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                float m = v[0];
+#pragma unroll
+                for (int j = 1; j < 16; ++j) m = fmaxf(m, v[j]);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+                float run = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    run += expf(v[j] - m);
+                    v[j] = run;
+                }
+                float incl = run;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float tt = __shfl_up_sync(0xffffffffu, incl, off);
+                    if (lane >= off) incl += tt;
+                }
+                const float excl = incl - run;
+                const float total = __shfl_sync(0xffffffffu, incl, 31);
+                float uu = 0.f, fx = 0.f;
+                if (lane == 0 && fl < nf) {
+                    uu = p.uniforms ? p.uniforms[(size_t)t * p.B + bglob] : philox_u01(p.seed, t, bglob);
+                    if (p.forced_x) fx = p.forced_x[(size_t)t * p.B + bglob];
+                }
+                uu = __shfl_sync(0xffffffffu, uu, 0);
+                fx = __shfl_sync(0xffffffffu, fx, 0);
+                const float thr = uu * total;
+                int cnt = 0;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) cnt += (excl + v[j] <= thr) ? 1 : 0;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
+                const int kk = cnt > NCLASS - 1 ? NCLASS - 1 : cnt;
+                const float sample = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, (float)kk), (float)NCLASS - 1.0f), 1.0f);   // :214
+                if (lane == 0 && fl < nf) {
+                    p.samples_out[(size_t)bglob * S + t] = sample;
+                    if (p.labels_out) p.labels_out[(size_t)bglob * S + t] = kk;
+                }
+                const float xnext = fl < nf ? (p.forced_x ? fx : sample) : 0.f;
+                if (lane < CL) {                                // lane d delivers x to CTA d
+                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa(sb + SM_X + fl * 4, (uint32_t)lane)), "f"(xnext) : "memory");
+                    mbar_arrive_remote(mapa(bar0 + B_X * 8, (uint32_t)lane));
+                }
+            }
+        }
+    }
+    // ---- teardown: every role is done (or timed out); peers may still be writing into this CTA until the cluster barrier
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+}   // namespace wrnn_dense

@@ -36,7 +36,7 @@ typedef enum {
 } wrnn_status;
 
 enum { WRNN_MODE_RAW = 0, WRNN_MODE_MOL = 1 };
-enum { WRNN_PREC_FP32 = 0, WRNN_PREC_BF16 = 1 };
+enum { WRNN_PREC_FP32 = 0, WRNN_PREC_BF16 = 1, WRNN_PREC_BF16_DENSE = 2 };
 
 /* Model geometry: WaveRNN.__init__, fatchord_version.py:90-114. */
 typedef struct {
@@ -46,8 +46,13 @@ typedef struct {
     int32_t aux_dims;    /* res_out_dims / 4 = 32 (fatchord_version.py:104) */
     int32_t n_classes;   /* 2**bits (RAW) or 30 (MOL) (fatchord_version.py:96-99) */
     int32_t mode;        /* WRNN_MODE_* */
-    int32_t precision;   /* WRNN_PREC_*: storage of the RESIDENT WEIGHTS (bf16 = rounded after the fp64 folding of the
-                            input layer); activations, accumulation and the exchange stay fp32 in both */
+    int32_t precision;   /* WRNN_PREC_FP32 / WRNN_PREC_BF16: storage of the RESIDENT WEIGHTS of the persistent FFMA kernel
+                            (bf16 = rounded after the fp64 folding of the input layer); activations, accumulation and
+                            the exchange stay fp32 in both.
+                            WRNN_PREC_BF16_DENSE: the dense-regime kernel (north star: "tcgen05 tensor-core tiles when
+                            the fold batch makes the per-step matmul dense"): bf16 weights streamed from L2 by TMA,
+                            bf16 activations, fp32 accumulation in tensor memory, fp32 recurrent state and sampling;
+                            clusters of 8 CTAs advance 32 folds each, 500+ folds in flight per GPU.  RAW 512 classes. */
 } wrnn_config;
 
 /* The sixteen state_dict tensors on the step path, torch [out, in] row-major fp32, HOST memory
@@ -83,6 +88,15 @@ int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w /* [host] */);
 int64_t wrnn_packed_floats(const wrnn_config *cfg);
 int32_t wrnn_pack_weights_host(const wrnn_config *cfg, const wrnn_weights *w /* [host] */,
                                float *out /* [host] */, int64_t out_floats);
+
+/* Host-only view of the WRNN_PREC_BF16_DENSE repack (no GPU needed), used by the CPU tests to replay the kernel's
+ * tensor-core program in numpy.  layout[8] = {bundles per step, stream bytes per CTA rank, sizeof(bundle record),
+ * CTAs per cluster, units per CTA, folds per cluster, per-row vectors, 0}.  stream: [cluster CTAs][stream bytes] bf16
+ * operand tiles in issue order; table: the bundle records (csrc/wavernn_dense.cuh::Bundle); sv: fp32
+ * [cluster CTAs][vectors][units per CTA] biases and sample coefficients. */
+int32_t wrnn_dense_layout(const wrnn_config *cfg, int64_t *layout /* [host] int64[8] */);
+int32_t wrnn_dense_pack_host(const wrnn_config *cfg, const wrnn_weights *w /* [host] */,
+                             uint8_t *stream /* [host] */, uint8_t *table /* [host] */, float *sv /* [host] */);
 
 /* fold_with_overlap index arithmetic, fatchord_version.py:298-309 (pure host integer code).
  * num_folds may be 0 (total_len <= overlap).  padded_len is the reference's padded length. */
