@@ -59,6 +59,7 @@ struct wrnn_handle {
     unsigned char *dense_stream = nullptr;
     wrnn_dense::Bundle *dense_table = nullptr;
     float *dense_sv = nullptr;
+    long long *dense_prof = nullptr;       // [clusters * CL][PROF_N], development profiling
 };
 
 extern "C" int32_t wrnn_abi_version(void) { return WRNN_ABI_VERSION; }
@@ -188,6 +189,7 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
             return fail(WRNN_ERR_CUDA, "dense kernel needs %d B shared memory, device allows %d", wrnn_dense::SM_TOTAL, h->smem_limit);
         }
         H_TRY(cudaFuncSetAttribute(wrnn_dense::wavernn_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wrnn_dense::SM_TOTAL));
+        H_TRY(cudaFuncSetAttribute(wrnn_dense::wavernn_dense_kernel_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, wrnn_dense::SM_TOTAL));
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(wrnn_dense::CL * 64);
         lc.blockDim = dim3(wrnn_dense::DTHREADS);
@@ -217,6 +219,7 @@ extern "C" void wrnn_destroy(wrnn_handle *h)
     cudaFree(h->dense_stream);
     cudaFree(h->dense_table);
     cudaFree(h->dense_sv);
+    cudaFree(h->dense_prof);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     delete h;
@@ -375,10 +378,10 @@ static void finish_images(int rows5, int bf16w, const std::vector<float> &img32,
 
 // ---- precision bf16-dense: operand stream, bundle table and per-row vectors of csrc/wavernn_dense.cuh ------------
 // One step of the tensor-core program, in issue order (wavernn_dense.cuh has the dependency argument):
-//   (a) after h1(t):  Wih2x.h1 -> g2 [commit G2] | Wfc1x.h1 -> f1 | Whh1.h1 -> g1 (first touch: step t+1)
+//   (a) after h1(t):  Wih2x.h1 -> g2 [commit G2] | Wfc1x.h1 -> f1
 //   (b) after h2(t):  Wfc1x.h2 -> f1 [commit F1] | Whh2.h2 -> g2 (first touch: step t+1)
-//   (c) after y1(t):  Wfc2x.y1 -> f2 [commit F2] | after cond(t+1): P1 -> g1, P3 -> f1 (first touch), P2 -> g2
-//   (d) after y2(t):  Wfc3.y2 -> f3 (first touch) [commit F3] | P4 -> f2 (first touch) [commit G1]
+//   (c) after y1(t):  Wfc2x.y1 -> f2 [commit F2] | after cond(t+1): P1 -> g1 (first touch), P3 -> f1 (first touch), P2 -> g2
+//   (d) after y2(t):  Wfc3.y2 -> f3 (first touch) [commit F3] | P4 -> f2 (first touch) | Whh1.h1 -> g1 (step t+1) [commit G1]
 // Tiles: T0 = [r | z] rows of the CTA's 64 units (128 rows), T1 = the n rows (64), F = 64 fc rows / classes.
 namespace {
 using wrnn_dense::Bundle;
@@ -455,7 +458,6 @@ static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
     // (a)
     hidden(W_H1, C_G2, IMG_H1, w->r2_wih, RA, D_G2_T0, D_G2_1I, 0, 0);
     fc(W_NONE, C_NONE, IMG_H1, w->fc1_w, RA, D_F1, 0, false);
-    hidden(W_NONE, C_NONE, IMG_H1, w->r1_whh, R, D_G1_T0, D_G1_1H, 1, 1);
     // (b)
     fc(W_H2, C_F1, IMG_H2, w->fc1_w, RA, D_F1, 0, false);
     hidden(W_NONE, C_NONE, IMG_H2, w->r2_whh, R, D_G2_T0, D_G2_1H, 1, 1);
@@ -468,7 +470,7 @@ static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
         DenseBundle c3;
         c3.wait = W_COND;
         c3.commit = C_NONE;
-        c3.segs.push_back(DenseSeg(128, 7, cnd(0), D_G1_T0, 0, [=](int rank, int m, int k) { return g1[(size_t)rowT0(rank, m) * KC + k]; }));
+        c3.segs.push_back(DenseSeg(128, 7, cnd(0), D_G1_T0, 1, [=](int rank, int m, int k) { return g1[(size_t)rowT0(rank, m) * KC + k]; }));
         prog.push_back(c3);
         DenseBundle c4;
         c4.wait = W_NONE;
@@ -492,9 +494,11 @@ static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
         fc(W_Y2, C_F3, IMG_Y2, w->fc3_w, R, D_F3, 1, true);
         DenseBundle d3;
         d3.wait = W_NONE;
-        d3.commit = C_G1;
+        d3.commit = C_NONE;
         d3.segs.push_back(DenseSeg(UPC, 2, cnd(22), D_F2, 1, [=](int rank, int m, int k) { return (double)f2[(size_t)unit(rank, m) * RA + R + k]; }));
         prog.push_back(d3);
+        // Whh1.h1(t) for step t+1 fills the tensor pipe while the logits are exchanged and sampled
+        hidden(W_NONE, C_G1, IMG_H1, w->r1_whh, R, D_G1_T0, D_G1_1H, 0, 1);
     }
     if ((int)prog.size() > MAXBUNDLE) return fail(WRNN_ERR_INVALID, "dense program has %zu bundles (max %d)", prog.size(), MAXBUNDLE);
 
@@ -751,12 +755,15 @@ extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const 
         // every launch keeps as many clusters busy as fit at once; folds are dealt evenly, at most BC per cluster
         using namespace wrnn_dense;
         if (cond_rows > 0x7fffffffll) return fail(WRNN_ERR_INVALID, "dense path indexes conditioning rows with 32 bits (got %lld rows)", (long long)cond_rows);
-        const int cap = h->dense_clusters * BC;
+        // clusters are independent (no grid-level synchronisation): one launch holds every fold, the hardware runs the
+        // clusters in waves of h->dense_clusters
+        const int cap = 2048 * BC;
         for (int b0 = 0; b0 < num_folds; b0 += cap) {
             const int nb = num_folds - b0 < cap ? num_folds - b0 : cap;
+            // whole waves of co-resident clusters, folds dealt evenly: a cluster's step time hardly depends on its fold count
             int ncl = (nb + BC - 1) / BC;
-            const char *spread = getenv("WRNN_DENSE_SPREAD");      // development knob: use every cluster even for few folds
-            if (spread && atoi(spread) > 0) ncl = nb < h->dense_clusters ? nb : h->dense_clusters;
+            if (ncl > h->dense_clusters) ncl = (ncl + h->dense_clusters - 1) / h->dense_clusters * h->dense_clusters;
+            if (ncl > nb) ncl = nb;
             DParams dp;
             memset(&dp, 0, sizeof dp);
             dp.wstream = h->dense_stream;
@@ -780,9 +787,15 @@ extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const 
             dp.fold0 = b0;
             dp.nfolds = nb;
             dp.per = (nb + ncl - 1) / ncl;
+            if (h->profiling) {
+                if (!h->dense_prof) CUDA_TRY(cudaMalloc(&h->dense_prof, (size_t)h->dense_clusters * CL * PROF_N * sizeof(long long)));
+                CUDA_TRY(cudaMemsetAsync(h->dense_prof, 0, (size_t)h->dense_clusters * CL * PROF_N * sizeof(long long), st));
+                dp.prof = h->dense_prof;
+            }
             CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
             CUDA_TRY(cudaEventRecord(h->ev0, st));
-            wavernn_dense_kernel<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
+            if (dp.prof) wavernn_dense_kernel_prof<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
+            else wavernn_dense_kernel<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
             CUDA_TRY(cudaGetLastError());
             CUDA_TRY(cudaEventRecord(h->ev1, st));
             CUDA_TRY(cudaStreamSynchronize(st));
@@ -852,6 +865,10 @@ extern "C" int32_t wrnn_set_profiling(wrnn_handle *h, int32_t enable)
 {
     if (!h) return fail(WRNN_ERR_INVALID, "null handle");
     CUDA_TRY(cudaSetDevice(h->device));
+    if (h->dense) {
+        h->profiling = enable != 0;
+        return WRNN_OK;
+    }
     if (enable && !h->prof_dev) CUDA_TRY(cudaMalloc(&h->prof_dev, (size_t)NCTA * PROF_SLOTS * sizeof(long long)));
     h->profiling = enable != 0;
     return WRNN_OK;
@@ -860,6 +877,13 @@ extern "C" int32_t wrnn_set_profiling(wrnn_handle *h, int32_t enable)
 extern "C" int32_t wrnn_get_stage_cycles(wrnn_handle *h, int64_t *out, int32_t n)
 {
     if (!h || !out) return fail(WRNN_ERR_INVALID, "null argument");
+    if (h->dense) {     // dense kernel: [CTAs of the last launch capacity][32] counters, slot map in csrc/wavernn_dense.cuh
+        if (!h->dense_prof) return fail(WRNN_ERR_STATE, "profiling was never enabled");
+        const int have = h->dense_clusters * wrnn_dense::CL * wrnn_dense::PROF_N;
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaMemcpy(out, h->dense_prof, (size_t)(n < have ? n : have) * sizeof(long long), cudaMemcpyDeviceToHost));
+        return WRNN_OK;
+    }
     if (!h->prof_dev) return fail(WRNN_ERR_STATE, "profiling was never enabled");
     if (n != NCTA * PROF_SLOTS) return fail(WRNN_ERR_INVALID, "n must be %d", NCTA * PROF_SLOTS);
     CUDA_TRY(cudaSetDevice(h->device));

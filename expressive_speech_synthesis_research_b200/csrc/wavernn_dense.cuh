@@ -93,7 +93,11 @@ struct DParams {
     int nb;                        // bundles per step
     int B, S;                      // folds of the whole call (row stride of uniforms / logits), steps
     int fold0, nfolds, per;        // this launch: folds [fold0, fold0 + nfolds), `per` per cluster
+    long long *prof;               // optional [CTAs][PROF_N] cycle counters (development), else nullptr
 };
+constexpr int PROF_N = 32;
+// profile slots: MMA thread 0-4 wait H1/H2/Y1/Y2/COND, 5 wait ring full, 6 issue, 7 total | epilogue (thread 0) 8-12 wait
+// G1/G2/F1/F2/F3, 13 wait x, 14 wait logits, 15-19 stages E1..E5, 20 sampling, 21 conditioning, 22 total | producer 0: 24 wait empty, 25 total
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -141,9 +145,12 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+// D[tmem] (+)= A[smem desc] * B[smem desc]; descriptors are passed as their 32-bit halves so that stepping along K is one
+// 32-bit add on the address field (the issuing thread's instruction latency is what paces short MMAs)
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t accumulate)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate));
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])
 {
@@ -155,16 +162,18 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16])
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, no swizzle: core matrix = 8 rows x 16 B stored contiguously (128 B),
 // LBO = byte distance between the two core matrices of a k-step along K, SBO = between 8-row groups (128 B here)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes)
-{
-    const uint32_t lo = ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
-    const uint32_t hi = (128u >> 4) | (1u << 14);            // SBO | descriptor version 1 (Blackwell)
-    return ((uint64_t)hi << 32) | lo;
-}
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t addr, uint32_t lbo_bytes) { return ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);       // SBO = 128 B | descriptor version 1 (Blackwell)
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BC
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
@@ -226,17 +235,19 @@ __device__ __forceinline__ void cond_store(uint8_t *cond_img, int tid, const Con
     }
 }
 
-// broadcast this CTA's 4 KB slice of activation image `img` to the 7 peers (one thread)
-__device__ __forceinline__ void send_slice(uint32_t smem_base, int img, uint32_t rank)
+// broadcast this CTA's 4 KB slice of activation image `img` to the 7 peers: called by warp 0, lane q > 0 serves peer
+// rank + q (issuing a bulk copy stalls the issuing thread, so the seven copies are issued by seven lanes), lane 0 arms
+// the CTA's own barrier with the bytes it expects from its peers
+__device__ __forceinline__ void send_slice(uint32_t smem_base, int img, uint32_t rank, int lane)
 {
     const uint32_t src = smem_base + SM_IMG + img * IMG_B + rank * SLICE_B;
     const uint32_t bar = smem_base + SM_BAR + (B_ACT + img) * 8;
-    mbar_expect_tx(bar, (CL - 1) * SLICE_B);
-#pragma unroll 1
-    for (uint32_t q = 1; q < CL; ++q) {
-        const uint32_t peer = (rank + q) & (CL - 1);
+    if (lane == 0) mbar_expect_tx(bar, (CL - 1) * SLICE_B);
+    else if (lane < CL) {
+        const uint32_t peer = (rank + (uint32_t)lane) & (CL - 1);
         bulk_s2peer(mapa(src, peer), src, SLICE_B, mapa(bar, peer));
     }
+    __syncwarp();
 }
 
 // GRU epilogue of one layer (torch.nn.GRUCell, fatchord_version.py:190,194): lanes 0-63 of the accumulators hold
@@ -314,7 +325,8 @@ __device__ __forceinline__ void fc_epilogue(uint32_t tmem, int col, uint8_t *sme
     epi_sync();
 }
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavernn_dense_kernel(const DParams p)
+template <bool PROF>
+__device__ __forceinline__ void dense_body(const DParams &p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -370,21 +382,33 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavern
             const uint32_t full = bar0 + (B_FULL + pw) * 8, empty = bar0 + (B_EMPTY + pw) * 8, dst = sb + SM_RING + pw * SLOT;
             const long long total = (long long)(S + 1) * p.nb;
             int b = pw;                                         // bundle index within the step
+            long long t_empty = 0;
+            const long long t_begin = clock64();
             for (long long gb = pw, use = 0; gb < total; gb += NSLOT, ++use) {
+                const long long t0 = PROF ? clock64() : 0;
                 if (use > 0 && !mbar_wait(empty, (unsigned)((use - 1) & 1), p.status, 1)) break;
+                if (PROF) t_empty += clock64() - t0;
                 const uint32_t bytes = tab[b].bytes;
                 mbar_expect_tx(full, bytes);
                 bulk_g2s(dst, src + tab[b].src_off, bytes, full);
                 b += NSLOT;
                 if (b >= p.nb) b -= p.nb;
             }
+            if (PROF && p.prof && pw == 0) {
+                p.prof[(size_t)blockIdx.x * PROF_N + 24] = t_empty;
+                p.prof[(size_t)blockIdx.x * PROF_N + 25] = clock64() - t_begin;
+            }
         }
     } else if (warp == MMA_WARP) {
-        // ===== MMA issue: one thread walks the bundle table once per step; t = -1 primes the accumulators of step 0
-        if (lane == 0) {
+        // ===== MMA issue: the whole warp walks the bundle table once per step (warp-uniform control flow and operands, so the
+        // descriptors live in uniform registers); one elected lane issues.  t = -1 primes the accumulators of step 0
+        {
+            const bool leader = elect_one();
             unsigned ph_full = 0, ph_wait = 0;                  // phase bits: ring slots / wait events
             long long gb = 0;
             bool ok = true;
+            long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const long long t_begin = clock64();
             for (int t = -1; t < S && ok; ++t) {
                 const bool pre = t < 0;
                 for (int b = 0; b < p.nb && ok; ++b, ++gb) {
@@ -392,30 +416,52 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavern
                     const int w = bd.wait;
                     if (w != W_NONE && (w == W_COND || !pre)) {
                         const uint32_t wb = w == W_COND ? bar0 + B_COND * 8 : bar0 + (B_ACT + (w - W_H1)) * 8;
+                        const long long t0 = PROF ? clock64() : 0;
                         ok = mbar_wait(wb, (ph_wait >> w) & 1u, p.status, 10 + w);
+                        if (PROF) pf[w - 1] += clock64() - t0;
                         ph_wait ^= 1u << w;
                         if (!ok) break;
                     }
                     const int slot = (int)(gb & 1);
+                    const long long t1 = PROF ? clock64() : 0;
                     ok = mbar_wait(bar0 + (B_FULL + slot) * 8, (ph_full >> slot) & 1u, p.status, 2);
+                    const long long t2 = PROF ? clock64() : 0;
+                    if (PROF) pf[5] += t2 - t1;
                     ph_full ^= 1u << slot;
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t slot_base = sb + SM_RING + slot * SLOT;
                     for (int s = 0; s < bd.nseg; ++s) {
                         const Seg sg = bd.seg[s];
-                        const uint32_t a0 = slot_base + (uint32_t)sg.off16 * 16, b0 = sb + SM_IMG + (uint32_t)sg.bsrc16 * 16;
-                        const uint32_t lbo_a = (uint32_t)sg.rows * 16, step_a = (uint32_t)sg.rows * 32;
-                        for (int k = 0; k < sg.nk; ++k)
-                            tc_mma(tmem + sg.dcol, smem_desc(a0 + k * step_a, lbo_a), smem_desc(b0 + k * 2 * CHUNK_B, CHUNK_B), IDESC, (k > 0 || !sg.first) ? 1u : 0u);
+                        const uint32_t rows = sg.rows, d = tmem + sg.dcol;
+                        uint32_t a_lo = smem_desc_lo(slot_base + (uint32_t)sg.off16 * 16, rows * 16);
+                        uint32_t b_lo = smem_desc_lo(sb + SM_IMG + (uint32_t)sg.bsrc16 * 16, CHUNK_B);
+                        const uint32_t a_inc = rows * 2;                      // one k-step = 2 chunks of rows x 16 B, in 16-byte units
+                        constexpr uint32_t b_inc = 2 * CHUNK_B / 16;
+                        if (leader) tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, sg.first ? 0u : 1u);
+                        const int nk = sg.nk;
+#pragma unroll 4
+                        for (int k = 1; k < nk; ++k) {
+                            a_lo += a_inc;
+                            b_lo += b_inc;
+                            if (leader) tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, 1u);
+                        }
                     }
-                    tc_commit(bar0 + (B_EMPTY + slot) * 8);
                     const int c = bd.commit;
-                    if (c != C_NONE && (c == C_G1 || !pre)) tc_commit(bar0 + (B_ACC + (c == C_G1 ? 0 : c)) * 8);
+                    if (leader) {
+                        tc_commit(bar0 + (B_EMPTY + slot) * 8);
+                        if (c != C_NONE && (c == C_G1 || !pre)) tc_commit(bar0 + (B_ACC + (c == C_G1 ? 0 : c)) * 8);
+                    }
+                    __syncwarp();
+                    if (PROF) pf[6] += clock64() - t2;
                 }
             }
-            tc_commit(bar0 + B_DONE * 8);
+            if (leader) tc_commit(bar0 + B_DONE * 8);
+            __syncwarp();
             mbar_wait(bar0 + B_DONE * 8, 0, p.status, 3);
+            pf[7] = clock64() - t_begin;
+            if (PROF && p.prof && leader)
+                for (int i = 0; i < 8; ++i) p.prof[(size_t)blockIdx.x * PROF_N + i] = pf[i];
         }
     } else {
         // ===== epilogue warps =====
@@ -442,50 +488,64 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavern
 
         unsigned ph = 0;                                        // phase bits of B_ACC + {0..4}, B_X (bit 5), B_LG (bit 6)
         bool ok = true;
+        long long pe[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tk = clock64();
+        const long long te_begin = tk;
+#define TICK(slot) do { if (PROF) { const long long now_ = clock64(); pe[slot] += now_ - tk; tk = now_; } } while (0)
         for (int t = 0; t < S && ok; ++t) {
             // ---- E1: h1(t) = GRU1(I(x(t-1), c(t)), h1(t-1)) -- fatchord_version.py:188-190
             ok = mbar_wait(bar0 + (B_ACC + 0) * 8, ph & 1u, p.status, 20);
             ph ^= 1u;
             if (!ok) break;
+            TICK(0);
             if (t > 0) {
                 ok = mbar_wait(bar0 + B_X * 8, (ph >> 5) & 1u, p.status, 25);
                 ph ^= 1u << 5;
                 if (!ok) break;
             }
+            TICK(5);
             tc_fence_after();
             gru_epilogue(tmem, D_G1_T0, D_G1_1H, D_G1_1I, smem, IMG_H1, rank, warp, lane, b1r, u1r, b1ni, u1n, b1nh, b1z, u1z, h1);
-            if (tid == 0) send_slice(sb, IMG_H1, rank);
+            if (warp == 0) send_slice(sb, IMG_H1, rank, lane);
+            TICK(7);
             // conditioning of step t+1 -> image (all MMAs that read the image of step t completed before the G1 commit)
             cond_store(cond_img, tid, cr);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + B_COND * 8);
             cond_load(p, fold_row0, fold_lim, nf, tid, t + 2, cr);
+            TICK(13);
             // ---- E2: h2(t) = GRU2([x + h1, a2], h2(t-1)) -- :192-194
             ok = mbar_wait(bar0 + (B_ACC + C_G2) * 8, (ph >> C_G2) & 1u, p.status, 21);
             ph ^= 1u << C_G2;
             if (!ok) break;
+            TICK(1);
             tc_fence_after();
             gru_epilogue(tmem, D_G2_T0, D_G2_1H, D_G2_1I, smem, IMG_H2, rank, warp, lane, b2r, u2r, b2ni, u2n, b2nh, b2z, u2z, h2);
-            if (tid == 0) send_slice(sb, IMG_H2, rank);
+            if (warp == 0) send_slice(sb, IMG_H2, rank, lane);
+            TICK(8);
             // ---- E3: y1 = relu(fc1([x + h1 + h2, a3])) -- :196-198
             ok = mbar_wait(bar0 + (B_ACC + C_F1) * 8, (ph >> C_F1) & 1u, p.status, 22);
             ph ^= 1u << C_F1;
             if (!ok) break;
+            TICK(2);
             tc_fence_after();
             fc_epilogue(tmem, D_F1, smem, IMG_Y1, rank, warp, lane, b3, u3);
-            if (tid == 0) send_slice(sb, IMG_Y1, rank);
+            if (warp == 0) send_slice(sb, IMG_Y1, rank, lane);
+            TICK(9);
             // ---- E4: y2 = relu(fc2([y1, a4])) -- :200-201
             ok = mbar_wait(bar0 + (B_ACC + C_F2) * 8, (ph >> C_F2) & 1u, p.status, 23);
             ph ^= 1u << C_F2;
             if (!ok) break;
+            TICK(3);
             tc_fence_after();
             fc_epilogue(tmem, D_F2, smem, IMG_Y2, rank, warp, lane, b4, 0.0f);
-            if (tid == 0) send_slice(sb, IMG_Y2, rank);
+            if (warp == 0) send_slice(sb, IMG_Y2, rank, lane);
+            TICK(10);
             // ---- E5: logits = fc3(y2) (:202): this CTA's 64 classes of every fold -> the CTA that samples the fold
             ok = mbar_wait(bar0 + (B_ACC + C_F3) * 8, (ph >> C_F3) & 1u, p.status, 24);
             ph ^= 1u << C_F3;
             if (!ok) break;
+            TICK(4);
             tc_fence_after();
             if (q < 2) {
                 const int hf = warp >> 2;
@@ -499,18 +559,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavern
             }
             tc_fence_before();
             epi_sync();
-            if (tid == 0) {
+            if (warp == 0) {                                    // lane d < CL: folds FPC d .. FPC d + FPC - 1 are sampled by CTA d
                 const uint32_t lgbar = bar0 + B_LG * 8;
-                mbar_expect_tx(lgbar, CL * FPC * UPC * 4);
-#pragma unroll 1
-                for (uint32_t d = 0; d < CL; ++d)               // folds FPC d .. FPC d + FPC - 1 are sampled by CTA d
-                    bulk_s2peer(mapa(sb + SM_SAMP + rank * (FPC * UPC * 4), d), sb + SM_SCRATCH + d * (FPC * UPC * 4), FPC * UPC * 4, mapa(lgbar, d));
+                if (lane == 0) mbar_expect_tx(lgbar, CL * FPC * UPC * 4);
+                __syncwarp();
+                if (lane < CL)
+                    bulk_s2peer(mapa(sb + SM_SAMP + rank * (FPC * UPC * 4), (uint32_t)lane), sb + SM_SCRATCH + lane * (FPC * UPC * 4), FPC * UPC * 4, mapa(lgbar, (uint32_t)lane));
+                __syncwarp();
             }
+            TICK(11);
             // ---- sampling (:210-216): warp w < FPC takes fold FPC rank + w; softmax + inverse CDF as in the fp32 kernel
             if (warp < FPC) {
                 ok = mbar_wait(bar0 + B_LG * 8, (ph >> 6) & 1u, p.status, 26);
                 ph ^= 1u << 6;
                 if (!ok) break;
+                TICK(6);
                 const int fl = FPC * (int)rank + warp;          // fold within the cluster
                 const int bglob = cfold0 + fl;
                 const float *lg = reinterpret_cast<const float *>(smem + SM_SAMP) + ((lane >> 2) * FPC + warp) * UPC + (lane & 3) * 16;
@@ -568,7 +631,15 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavern
                     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa(sb + SM_X + fl * 4, (uint32_t)lane)), "f"(xnext) : "memory");
                     mbar_arrive_remote(mapa(bar0 + B_X * 8, (uint32_t)lane));
                 }
+                TICK(12);
             }
+        }
+#undef TICK
+        if (PROF && p.prof && tid == 0) {
+            // waits: 8-12 acc G1/G2/F1/F2/F3, 13 x, 14 logits | work: 15-19 E1..E5, 20 sampling, 21 conditioning
+            static const int map[14] = {8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21};
+            for (int i = 0; i < 14; ++i) p.prof[(size_t)blockIdx.x * PROF_N + map[i]] = pe[i];
+            p.prof[(size_t)blockIdx.x * PROF_N + 22] = clock64() - te_begin;
         }
     }
     // ---- teardown: every role is done (or timed out); peers may still be writing into this CTA until the cluster barrier
@@ -577,5 +648,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavern
     cluster_sync_all();
     if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
+
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavernn_dense_kernel(const DParams p) { dense_body<false>(p); }
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavernn_dense_kernel_prof(const DParams p) { dense_body<true>(p); }
 
 }   // namespace wrnn_dense

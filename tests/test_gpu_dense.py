@@ -1,0 +1,123 @@
+"""GPU parity of precision "bf16-dense" (tcgen05 / tensor-memory step loop, csrc/wavernn_dense.cuh), called through the
+C ABI and through generate(), against the fp64 oracle.  Tolerances are bf16 tolerances and are written here:
+  teacher-forced logits   max |dense - oracle fp64| <= TOL_DENSE_LOGITS   (logits of the synthetic model are O(0.3))
+  sampling                every label is the inverse-CDF outcome of the kernel's OWN logits (window TOL_DENSE_CDF)
+  free running            on the dense path's own history the fp64 oracle draws the same class up to +-DENSE_LABEL_SLACK
+Fold-level work is bit-reproducible: pooling / chunking / cluster placement must not change a fold's labels."""
+import numpy as np
+import pytest
+import torch
+
+from expressive_speech_synthesis_research_b200 import WaveRNN
+from oracle import c_oracle, synth
+from tests import helpers as H
+from tests.test_gpu_parity import run_folds
+
+pytestmark = pytest.mark.gpu
+
+TOL_DENSE_LOGITS = 5e-3
+TOL_DENSE_CDF = 1e-5
+DENSE_LABEL_SLACK = 4
+
+_M = {}
+
+
+def dense_model():
+    if "m" not in _M:
+        m = WaveRNN(**synth.model_kwargs("RAW", "ref"))
+        m.load_state_dict(synth.make_state("RAW", "ref", 0))
+        m = m.cuda()
+        m.precision = "bf16-dense"
+        _M["m"] = m
+    return _M["m"]
+
+
+def _inputs(B, S, seed):
+    rng = np.random.default_rng(seed)
+    mels = rng.uniform(0, 1, (B, S, 80)).astype(np.float32)
+    aux = rng.normal(0, 1, (B, S, 128)).astype(np.float32)
+    U = rng.uniform(0, 1, (S, B)).astype(np.float32)
+    return mels, aux, U
+
+
+def _own_cdf_margin(logits, U, labels):
+    lg = logits.astype(np.float64)
+    p = np.exp(lg - lg.max(-1, keepdims=True))
+    cdf = np.cumsum(p, -1) / p.sum(-1, keepdims=True)
+    k = labels.T.astype(np.int64)
+    hi = np.take_along_axis(cdf, k[..., None], -1)[..., 0]
+    lo = np.where(k > 0, np.take_along_axis(cdf, np.maximum(k - 1, 0)[..., None], -1)[..., 0], 0.0)
+    hi = np.where(k == lg.shape[-1] - 1, np.inf, hi)
+    u = U.astype(np.float64)
+    return np.maximum(lo - u, u - hi)
+
+
+def test_dense_teacher_forced_logits_vs_oracle():
+    m = dense_model()
+    sd = synth.make_state("RAW", "ref", 0)
+    B, S = 37, 48                                            # two clusters, ragged fold counts
+    mels, aux, U = _inputs(B, S, 11)
+    forced = np.random.default_rng(12).uniform(-1, 1, (S, B)).astype(np.float32)
+    r = run_folds(m, mels, aux, U, forced=forced, logits=True)
+    want = c_oracle.generate_folds(sd, "RAW", mels, aux, U, forced_x=forced, want_logits=True, precision="fp64")["logits"]
+    err = np.abs(r["logits"] - want).max()
+    assert err <= TOL_DENSE_LOGITS, err
+    assert _own_cdf_margin(r["logits"], U, r["labels"]).max() <= TOL_DENSE_CDF
+    assert np.array_equal(r["samples"], H.labels_to_float(r["labels"], 512))          # label -> float map is exact
+
+
+def test_dense_free_running_is_consistent_with_the_oracle():
+    m = dense_model()
+    sd = synth.make_state("RAW", "ref", 0)
+    B, S = 9, 300
+    mels, aux, U = _inputs(B, S, 21)
+    r = run_folds(m, mels, aux, U, logits=True)
+    assert _own_cdf_margin(r["logits"], U, r["labels"]).max() <= TOL_DENSE_CDF
+    # fp64 oracle teacher-forced on the dense path's own sample history: same logits within the bf16 tolerance at EVERY
+    # step of a free run (errors do not build up), and the classes it would draw are the dense ones up to a few levels
+    forced = r["samples"].T.copy()
+    o = c_oracle.generate_folds(sd, "RAW", mels, aux, U, forced_x=forced, want_logits=True, precision="fp64")
+    assert np.abs(r["logits"] - o["logits"]).max() <= TOL_DENSE_LOGITS
+    d = np.abs(o["labels"].astype(np.int64) - r["labels"].astype(np.int64))
+    assert d.max() <= DENSE_LABEL_SLACK, d.max()
+    assert (d == 0).mean() > 0.6, (d == 0).mean()
+
+
+def test_dense_pooling_chunking_and_placement_do_not_change_a_fold():
+    m = dense_model()
+    B, S = 70, 40
+    mels, aux, U = _inputs(B, S, 31)
+    whole = run_folds(m, mels, aux, U)["labels"]
+    a = run_folds(m, mels[:17], aux[:17], U[:, :17].copy())["labels"]
+    b = run_folds(m, mels[17:], aux[17:], U[:, 17:].copy())["labels"]
+    assert np.array_equal(whole, np.concatenate([a, b]))
+
+
+def test_dense_philox_is_reproducible_and_seed_dependent():
+    m = dense_model()
+    dev = torch.device("cuda", 0)
+    B, S = 5, 64
+    mels, aux, _ = _inputs(B, S, 41)
+    mu = torch.as_tensor(mels).reshape(B * S, -1).contiguous().to(dev)
+    au = torch.as_tensor(aux).reshape(B * S, -1).contiguous().to(dev)
+    starts = np.arange(B, dtype=np.int64) * S
+    eng = m._engine(dev)
+    runs = [m._run_folds(eng, dev, mu, au, starts, starts + S, S, None, seed, None, False)["labels"].cpu().numpy() for seed in (7, 7, 8)]
+    assert np.array_equal(runs[0], runs[1]) and not np.array_equal(runs[0], runs[2])
+
+
+def test_dense_generate_end_to_end_matches_assembly_of_its_own_samples():
+    """generate() on the dense path: same fold / crossfade / mu-law epilogue as the fp32 path (bit-exact vs the oracle's
+    assembly of the SAME per-fold samples), waveform shape and range as the reference's."""
+    m = dense_model()
+    g = synth.GEOMETRY["ref"]
+    T = 120
+    mel = synth.make_mel(T, 3)
+    target, overlap = 2000, 100
+    wav, ex = m.generate(mel, True, target, overlap, True, seed=5, return_samples=True)
+    hop = g["hop_length"]
+    assert wav.dtype == np.float64 and wav.shape == ((T - 1) * hop,)
+    assert np.isfinite(wav).all() and np.abs(wav).max() <= 1.0
+    samples = ex["samples"].cpu().numpy()
+    want = c_oracle.assemble(samples, True, target, overlap, 512, (T - 1) * hop, hop)
+    assert np.abs(wav - want).max() <= H.TOL_MULAW_ABS
