@@ -41,8 +41,12 @@ def parse():
     ap.add_argument("--geometry", default="fatchord", choices=list(GEOMETRY))
     ap.add_argument("--mode", default="RAW", choices=["RAW", "MOL"])
     ap.add_argument("--seconds", type=float, default=10.0)
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
-                    help="resident weight precision of the CUDA path (bf16 = BASELINE.json configs[2] comparison; the headline is fp32)")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16", "bf16-dense"],
+                    help="fp32 (headline) | bf16 resident weights of the FFMA kernel (BASELINE.json configs[2]) | bf16-dense: the "
+                         "tcgen05 / tensor-memory kernel for large fold batches")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-regime (pooled folds, tcgen05) measurement")
+    ap.add_argument("--dense-folds", type=int, default=480)
+    ap.add_argument("--dense-steps", type=int, default=2000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-sample-steps", type=int, default=1200)
     return ap.parse_args()
@@ -173,6 +177,46 @@ def run_reference(args):
     return 0
 
 
+def dense_regime(args, dev, state, pk):
+    """BASELINE.json configs[3]/[4] regime: hundreds of pooled folds per GPU (sentence sets, long-form).  Times the
+    step loop alone (wrnn_generate_folds, conditioning resident in HBM, in-kernel Philox draws) for the tcgen05 kernel
+    (precision bf16-dense) and for the fp32 FFMA kernel on the same folds."""
+    import numpy as np
+    import torch
+    from expressive_speech_synthesis_research_b200 import WaveRNN
+    B, S = args.dense_folds, args.dense_steps
+    g = torch.Generator(device="cpu").manual_seed(5)
+    mels = torch.rand(B * S, 80, generator=g).to(dev)
+    aux = torch.randn(B * S, 128, generator=g).to(dev)
+    starts = np.arange(B, dtype=np.int64) * S
+    out = {"workload": "configs[3]/[4] regime: %d pooled folds x %d steps, step loop only, conditioning resident in HBM (%.0f MB > L2)"
+                       % (B, S, B * S * 208 * 4 / 1e6)}
+    for prec in ("bf16-dense", "fp32"):
+        m = WaveRNN(**model_kwargs("RAW", args.geometry)).to(dev)
+        m.load_state_dict(state)
+        m.precision = prec
+        eng = m._engine(dev)
+        nb = B if prec == "bf16-dense" else min(B, 64)           # the FFMA kernel advances 64 folds per launch: time one launch
+        ms = []
+        for it in range(3):
+            m._run_folds(eng, dev, mels, aux, starts[:nb], starts[:nb] + S, S, None, 11 + it, None, False)
+            torch.cuda.synchronize()
+            ms.append(eng.info().last_kernel_ms)
+        t = min(ms[1:]) * 1e-3
+        out[prec] = {"folds": nb, "us_per_step": t / S * 1e6, "fold_steps_per_us": nb * S / t / 1e6,
+                     "samples_per_sec_raw": nb * S / t}
+        del m, eng
+    d = out["bf16-dense"]
+    tf = d["fold_steps_per_us"] * 1e6 * FLOP_PER_FOLD_STEP["RAW"] / 1e12
+    out["speedup_vs_fp32_kernel"] = d["fold_steps_per_us"] / out["fp32"]["fold_steps_per_us"]
+    out["roofline"] = {"bound": "tensor", "kernel": "wavernn_dense_kernel", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                       "frac": tf / pk["bf16_tflops"], "traffic": None,
+                       "note": "algorithmic FLOPs (8.14 MFLOP per fold-step); every tcgen05.mma is M=128 x N=32 x K=16 and is paced by "
+                               "its shared-memory operand reads (40 clk measured, scripts/umma_rate.cu), the step by the shared-memory "
+                               "port (weights cross it twice: TMA fill + MMA read) and the cluster exchange (DESIGN.md 10)"}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # this repo's CUDA path
 # ------------------------------------------------------------------------------------------------
@@ -272,11 +316,13 @@ def run_b200(args):
         fp32_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12
         lat_floor = 5 * t_sync if t_sync else None
         fma_floor = wl["folds"] * FLOP_PER_FOLD_STEP[args.mode] / (fp32_peak * 1e12) * 1e6
+        dense = args.precision == "bf16-dense"
         line = {
             "metric": "generated_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": n,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "f32 math, bf16 resident weights", "data": "synthetic",
+            "dtype": {"fp32": "f32", "bf16": "f32 math, bf16 resident weights", "bf16-dense": "bf16 tensor-core products, f32 accumulation / state / sampling"}[args.precision],
+            "data": "synthetic",
             "rtf": (t_dev / args.steps) / (wl["wave_len"] / wl["sr"]),
             "config": config_dict(args, wl, n),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(mel_host.numel() * 4),
@@ -284,7 +330,7 @@ def run_b200(args):
                     "rtf": (max(t_e2e, t_e2e_wall) / args.steps) / (wl["wave_len"] / wl["sr"])},
             "gpu_launches": int((info1.launches - info0.launches) + (info1.epilogue_launches - info0.epilogue_launches)),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "wavernn_persistent_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
+            "roofline": {"bound": "hbm", "kernel": "wavernn_dense_kernel" if dense else "wavernn_persistent_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
                          "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
                          "kernel_ms_per_launch": k_ms,
                          "note": "HBM is not what bounds this kernel (840 B per fold-step, measured dram traffic ~0.7 GB/s); "
@@ -296,6 +342,14 @@ def run_b200(args):
                                    "frac_of_floor": (max(lat_floor or 0.0, fma_floor) / us_per_step) if us_per_step else None,
                                    "achieved_tflops": fold_steps * FLOP_PER_FOLD_STEP[args.mode] / (k_ms * 1e-3) / 1e12},
         }
+        if dense:
+            line["step_latency_model"] = {"us_per_step": us_per_step, "folds": wl["folds"], "clusters": (wl["folds"] + 31) // 32,
+                                          "achieved_tflops": fold_steps * FLOP_PER_FOLD_STEP[args.mode] / (k_ms * 1e-3) / 1e12}
+        if n == 1 and not args.no_dense and not dense and args.mode == "RAW":
+            try:
+                line["dense_regime"] = dense_regime(args, dev, model.state_dict(), pk)
+            except Exception as e:  # pragma: no cover
+                line["dense_regime"] = {"failed": repr(e)}
         if n == 1 and not args.no_cpu_baseline:
             try:
                 vals, times, cores, desc = cpu_reference_sample(args, wl, model.state_dict(), 600, repeats=1, warmup=0)

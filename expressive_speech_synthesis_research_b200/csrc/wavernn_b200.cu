@@ -378,10 +378,11 @@ static void finish_images(int rows5, int bf16w, const std::vector<float> &img32,
 
 // ---- precision bf16-dense: operand stream, bundle table and per-row vectors of csrc/wavernn_dense.cuh ------------
 // One step of the tensor-core program, in issue order (wavernn_dense.cuh has the dependency argument):
-//   (a) after h1(t):  Wih2x.h1 -> g2 [commit G2] | Wfc1x.h1 -> f1
-//   (b) after h2(t):  Wfc1x.h2 -> f1 [commit F1] | Whh2.h2 -> g2 (first touch: step t+1)
-//   (c) after y1(t):  Wfc2x.y1 -> f2 [commit F2] | after cond(t+1): P1 -> g1 (first touch), P3 -> f1 (first touch), P2 -> g2
-//   (d) after y2(t):  Wfc3.y2 -> f3 (first touch) [commit F3] | P4 -> f2 (first touch) | Whh1.h1 -> g1 (step t+1) [commit G1]
+//   (a) after h1(t):  Wih2x.h1 -> g2 [commit G2] | Wfc1x.h1 -> f1 | P1.c(t+1) -> g1 (first touch)
+//   (b) after h2(t):  Wfc1x.h2 -> f1 [commit F1] | P2.c(t+1) -> g2 (first touch)
+//   (c) after y1(t):  Wfc2x.y1 -> f2 [commit F2] | P3.c(t+1) -> f1 (first touch)
+//   (d) after y2(t):  Wfc3.y2 -> f3 (first touch) [commit F3] | P4 -> f2 (first touch) | Whh1.h1 -> g1 [commit G1] | Whh2.h2 -> g2 [commit H2RD]
+// The part after each "|" is work for step t+1 placed where the tensor pipe would otherwise wait for an epilogue + exchange.
 // Tiles: T0 = [r | z] rows of the CTA's 64 units (128 rows), T1 = the n rows (64), F = 64 fc rows / classes.
 namespace {
 using wrnn_dense::Bundle;
@@ -455,51 +456,37 @@ static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
             prog.push_back(b);
         }
     };
-    // (a)
+    const double *g1 = G1.data(), *g2 = G2.data(), *g3 = G3.data();
+    const float *r2 = w->r2_wih, *f1 = w->fc1_w, *f2 = w->fc2_w;
+    auto p2 = [=](int row, int k) { return k < KC ? g2[(size_t)row * KC + k] : (double)r2[(size_t)row * RA + R + (k - KC)]; };
+    auto one = [&](int wait, int commit, std::vector<DenseSeg> segs) {
+        DenseBundle b;
+        b.wait = wait;
+        b.commit = commit;
+        b.segs = segs;
+        prog.push_back(b);
+    };
+    // conditioning inputs k: [0,80) mel | [80,112) a1 | [112,144) a2 | [144,176) a3 | [176,208) a4 (8 per image chunk)
+    // (a) critical: Wih2x.h1(t) -> g2.  Then, inside E2 + the h2 exchange: Wfc1x.h1 -> f1, P1.c(t+1) -> g1 (first touch)
     hidden(W_H1, C_G2, IMG_H1, w->r2_wih, RA, D_G2_T0, D_G2_1I, 0, 0);
     fc(W_NONE, C_NONE, IMG_H1, w->fc1_w, RA, D_F1, 0, false);
-    // (b)
+    one(W_COND, C_NONE, {DenseSeg(128, 7, cnd(0), D_G1_T0, 1, [=](int rank, int m, int k) { return g1[(size_t)rowT0(rank, m) * KC + k]; })});
+    one(W_NONE, C_NONE, {DenseSeg(UPC, 7, cnd(0), D_G1_1I, 1, [=](int rank, int m, int k) { return g1[(size_t)rowN(rank, m) * KC + k]; })});
+    // (b) critical: Wfc1x.h2(t) -> f1.  Inside E3 + the y1 exchange: P2.c(t+1) -> g2 (first touch; E2(t) has drained g2)
     fc(W_H2, C_F1, IMG_H2, w->fc1_w, RA, D_F1, 0, false);
-    hidden(W_NONE, C_NONE, IMG_H2, w->r2_whh, R, D_G2_T0, D_G2_1H, 1, 1);
-    // (c)
+    one(W_NONE, C_NONE, {DenseSeg(128, 8, cnd(0), D_G2_T0, 1, [=](int rank, int m, int k) { return p2(rowT0(rank, m), k); })});
+    one(W_NONE, C_NONE, {DenseSeg(128, 1, cnd(16), D_G2_T0, 0, [=](int rank, int m, int k) { return p2(rowT0(rank, m), 128 + k); }),
+                         DenseSeg(UPC, 9, cnd(0), D_G2_1I, 1, [=](int rank, int m, int k) { return p2(rowN(rank, m), k); })});
+    // (c) critical: Wfc2x.y1 -> f2.  Inside E4 + the y2 exchange: P3.c(t+1) -> f1 (first touch; E3(t) has drained f1)
     fc(W_Y1, C_F2, IMG_Y1, w->fc2_w, RA, D_F2, 0, false);
-    {   // conditioning projections of step t+1; cond k: [0,80) mel | [80,112) a1 | [112,144) a2 | [144,176) a3 | [176,208) a4
-        const double *g1 = G1.data(), *g2 = G2.data(), *g3 = G3.data();
-        const float *r2 = w->r2_wih, *f1 = w->fc1_w, *f2 = w->fc2_w;
-        auto p2 = [=](int row, int k) { return k < KC ? g2[(size_t)row * KC + k] : (double)r2[(size_t)row * RA + R + (k - KC)]; };
-        DenseBundle c3;
-        c3.wait = W_COND;
-        c3.commit = C_NONE;
-        c3.segs.push_back(DenseSeg(128, 7, cnd(0), D_G1_T0, 1, [=](int rank, int m, int k) { return g1[(size_t)rowT0(rank, m) * KC + k]; }));
-        prog.push_back(c3);
-        DenseBundle c4;
-        c4.wait = W_NONE;
-        c4.commit = C_NONE;
-        c4.segs.push_back(DenseSeg(UPC, 7, cnd(0), D_G1_1I, 1, [=](int rank, int m, int k) { return g1[(size_t)rowN(rank, m) * KC + k]; }));
-        c4.segs.push_back(DenseSeg(UPC, 7, cnd(0), D_F1, 1, [=](int rank, int m, int k) { return g3[(size_t)unit(rank, m) * KC + k]; }));
-        c4.segs.push_back(DenseSeg(UPC, 2, cnd(18), D_F1, 0, [=](int rank, int m, int k) { return (double)f1[(size_t)unit(rank, m) * RA + R + k]; }));
-        prog.push_back(c4);
-        DenseBundle c5;
-        c5.wait = W_NONE;
-        c5.commit = C_NONE;
-        c5.segs.push_back(DenseSeg(128, 8, cnd(0), D_G2_T0, 0, [=](int rank, int m, int k) { return p2(rowT0(rank, m), k); }));
-        prog.push_back(c5);
-        DenseBundle c6;
-        c6.wait = W_NONE;
-        c6.commit = C_NONE;
-        c6.segs.push_back(DenseSeg(128, 1, cnd(16), D_G2_T0, 0, [=](int rank, int m, int k) { return p2(rowT0(rank, m), 128 + k); }));
-        c6.segs.push_back(DenseSeg(UPC, 9, cnd(0), D_G2_1I, 1, [=](int rank, int m, int k) { return p2(rowN(rank, m), k); }));
-        prog.push_back(c6);
-        // (d)
-        fc(W_Y2, C_F3, IMG_Y2, w->fc3_w, R, D_F3, 1, true);
-        DenseBundle d3;
-        d3.wait = W_NONE;
-        d3.commit = C_NONE;
-        d3.segs.push_back(DenseSeg(UPC, 2, cnd(22), D_F2, 1, [=](int rank, int m, int k) { return (double)f2[(size_t)unit(rank, m) * RA + R + k]; }));
-        prog.push_back(d3);
-        // Whh1.h1(t) for step t+1 fills the tensor pipe while the logits are exchanged and sampled
-        hidden(W_NONE, C_G1, IMG_H1, w->r1_whh, R, D_G1_T0, D_G1_1H, 0, 1);
-    }
+    one(W_NONE, C_NONE, {DenseSeg(UPC, 7, cnd(0), D_F1, 1, [=](int rank, int m, int k) { return g3[(size_t)unit(rank, m) * KC + k]; }),
+                         DenseSeg(UPC, 2, cnd(18), D_F1, 0, [=](int rank, int m, int k) { return (double)f1[(size_t)unit(rank, m) * RA + R + k]; })});
+    // (d) critical: Wfc3.y2 -> f3.  Inside E5, the logits exchange, sampling and E1(t+1): P4 -> f2 (first touch), Whh1.h1(t) -> g1
+    // [commit G1: E1(t+1) may start], then Whh2.h2(t) -> g2 [commit H2RD: this CTA no longer reads the h2(t) image]
+    fc(W_Y2, C_F3, IMG_Y2, w->fc3_w, R, D_F3, 1, true);
+    one(W_NONE, C_NONE, {DenseSeg(UPC, 2, cnd(22), D_F2, 1, [=](int rank, int m, int k) { return (double)f2[(size_t)unit(rank, m) * RA + R + k]; })});
+    hidden(W_NONE, C_G1, IMG_H1, w->r1_whh, R, D_G1_T0, D_G1_1H, 0, 1);
+    hidden(W_NONE, C_H2RD, IMG_H2, w->r2_whh, R, D_G2_T0, D_G2_1H, 0, 1);
     if ((int)prog.size() > MAXBUNDLE) return fail(WRNN_ERR_INVALID, "dense program has %zu bundles (max %d)", prog.size(), MAXBUNDLE);
 
     // serialise: table (identical for every rank) and the per-rank streams

@@ -16,8 +16,9 @@
 // not depend on the value produced by the current stage is issued early ("deferred" segments), so the per-step
 // dependent chain is  E1 -> Wih2x.h1 -> E2 -> Wfc1x.h2 -> E3 -> Wfc2x.y1 -> E4 -> Wfc3.y2 -> E5 -> sample.
 //
-// Warp roles (352 threads): warps 0-7 epilogue (tensor memory -> registers -> gates / relu / sampling), warp 8 lane 0
-// issues every tcgen05.mma, warps 9 and 10 lane 0 stream the weight bundles (one ring slot each).
+// Warp roles (384 threads): warps 0-7 epilogue (tensor memory -> registers -> gates / relu / sampling), warp 8 issues every
+// tcgen05.mma (one elected lane), warps 9 and 10 lane 0 stream the weight bundles (one ring slot each), warp 11 lane 0
+// relays "h2 image no longer read" between the CTAs of the cluster.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -30,8 +31,8 @@ constexpr int DHID = 512;
 constexpr int UPC = DHID / CL;                 // hidden units (and RAW classes) per CTA
 constexpr int BC = 32;                        // folds per cluster = MMA N
 constexpr int NEPI = 256;                     // epilogue threads
-constexpr int MMA_WARP = 8, PROD_WARP0 = 9;
-constexpr int DTHREADS = NEPI + 96;
+constexpr int MMA_WARP = 8, PROD_WARP0 = 9, RELAY_WARP = 11;
+constexpr int DTHREADS = NEPI + 128;
 constexpr int SLOT = 32768, NSLOT = 2;        // weight ring
 constexpr int CHUNK_B = BC * 16;              // one k-chunk (8 k) of an activation image
 constexpr int IMG_B = (DHID / 8) * CHUNK_B;    // 32 KB: one activation image
@@ -45,7 +46,7 @@ constexpr int NSV = 18;                       // per-row fp32 vectors (biases, x
 
 enum { IMG_H1 = 0, IMG_H2 = 1, IMG_Y1 = 2, IMG_Y2 = 3 };
 enum { W_NONE = 0, W_H1 = 1, W_H2 = 2, W_Y1 = 3, W_Y2 = 4, W_COND = 5 };       // wait before a bundle
-enum { C_NONE = 0, C_G2 = 1, C_F1 = 2, C_F2 = 3, C_F3 = 4, C_G1 = 5 };         // commit after a bundle
+enum { C_NONE = 0, C_G2 = 1, C_F1 = 2, C_F2 = 3, C_F3 = 4, C_G1 = 5, C_H2RD = 6 };   // commit after a bundle
 // tensor-memory columns of the fp32 accumulators (BC columns each)
 enum { D_G1_T0 = 0, D_G1_1H = 32, D_G1_1I = 64, D_G2_T0 = 96, D_G2_1H = 128, D_G2_1I = 160, D_F1 = 192, D_F2 = 224, D_F3 = 256 };
 enum { DV_B1R = 0, DV_U1R, DV_B1Z, DV_U1Z, DV_B1NI, DV_U1N, DV_B1NH, DV_B2R, DV_U2R, DV_B2Z, DV_U2Z, DV_B2NI, DV_U2N, DV_B2NH, DV_B3, DV_U3, DV_B4, DV_B5 };
@@ -74,7 +75,7 @@ constexpr int SM_X = SM_SAMP + CL * FPC * UPC * 4;             // [BC] fp32 fed-
 constexpr int SM_FOLD = SM_X + BC * 4;                         // [2][BC] int32 first row / limit row
 constexpr int SM_TAB = SM_FOLD + 2 * BC * 4;
 constexpr int SM_BAR = SM_TAB + MAXBUNDLE * (int)sizeof(Bundle);
-enum { B_FULL = 0, B_EMPTY = 2, B_ACT = 4, B_LG = 8, B_X = 9, B_COND = 10, B_ACC = 11, B_DONE = 16, NBAR = 17 };
+enum { B_FULL = 0, B_EMPTY = 2, B_ACT = 4, B_LG = 8, B_X = 9, B_COND = 10, B_ACC = 11, B_DONE = 16, B_H2RD = 17, B_H2OK = 18, NBAR = 20 };   // B_H2OK: two barriers, alternating by step
 constexpr int SM_TMEM = SM_BAR + NBAR * 8;
 constexpr int SM_TOTAL = SM_TMEM + 16;
 
@@ -177,8 +178,10 @@ constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);       // SBO = 128 B | de
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BC
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 
-__device__ __forceinline__ float sigmoid_(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
-__device__ __forceinline__ float tanh_(float v) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * v)); }
+// one MUFU per gate (the GRU epilogues are MUFU-bound): tanh.approx has 2^-11 relative error, well inside the bf16 rounding
+// (2^-9) that every activation of this path goes through anyway
+__device__ __forceinline__ float tanh_(float v) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float sigmoid_(float v) { return fmaf(0.5f, tanh_(0.5f * v), 0.5f); }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 {
     const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
@@ -360,6 +363,9 @@ __device__ __forceinline__ void dense_body(const DParams &p)
         mbar_init(bar0 + B_COND * 8, NEPI / 32);
         for (int i = 0; i < 5; ++i) mbar_init(bar0 + (B_ACC + i) * 8, 1);
         mbar_init(bar0 + B_DONE * 8, 1);
+        mbar_init(bar0 + B_H2RD * 8, 1);
+        mbar_init(bar0 + B_H2OK * 8, CL);
+        mbar_init(bar0 + (B_H2OK + 1) * 8, CL);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -374,7 +380,17 @@ __device__ __forceinline__ void dense_body(const DParams &p)
     const uint32_t tmem = *reinterpret_cast<const uint32_t *>(smem + SM_TMEM);
     const int S = p.S;
 
-    if (warp >= PROD_WARP0) {
+    if (warp == RELAY_WARP) {
+        // ===== relay: once this CTA's Whh2.h2(t) products have completed (they read the h2(t) image long after the step's
+        // other users), tell every CTA of the cluster; a CTA broadcasts its slice of h2(t+1) only when all eight have
+        if (lane == 0) {
+            for (int t = -1; t < S; ++t) {
+                if (!mbar_wait(bar0 + B_H2RD * 8, (unsigned)((t + 1) & 1), p.status, 30)) break;
+#pragma unroll 1
+                for (uint32_t d = 0; d < CL; ++d) mbar_arrive_remote(mapa(bar0 + (B_H2OK + ((t + 1) & 1)) * 8, d));   // read by step t+1
+            }
+        }
+    } else if (warp >= PROD_WARP0) {
         // ===== weight stream: producer pw owns ring slot pw; bundle gb of the launch goes to slot gb & 1 =====
         if (lane == 0) {
             const int pw = warp - PROD_WARP0;
@@ -450,7 +466,8 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                     const int c = bd.commit;
                     if (leader) {
                         tc_commit(bar0 + (B_EMPTY + slot) * 8);
-                        if (c != C_NONE && (c == C_G1 || !pre)) tc_commit(bar0 + (B_ACC + (c == C_G1 ? 0 : c)) * 8);
+                        if (c == C_H2RD) tc_commit(bar0 + B_H2RD * 8);
+                        else if (c != C_NONE && (c == C_G1 || !pre)) tc_commit(bar0 + (B_ACC + (c == C_G1 ? 0 : c)) * 8);
                     }
                     __syncwarp();
                     if (PROF) pf[6] += clock64() - t2;
@@ -521,7 +538,10 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             TICK(1);
             tc_fence_after();
             gru_epilogue(tmem, D_G2_T0, D_G2_1H, D_G2_1I, smem, IMG_H2, rank, warp, lane, b2r, u2r, b2ni, u2n, b2nh, b2z, u2z, h2);
-            if (warp == 0) send_slice(sb, IMG_H2, rank, lane);
+            if (warp == 0) {                                    // every CTA has finished reading the h2(t-1) image (relay warp)
+                ok = mbar_wait(bar0 + (B_H2OK + (t & 1)) * 8, (unsigned)((t >> 1) & 1), p.status, 27);
+                send_slice(sb, IMG_H2, rank, lane);
+            }
             TICK(8);
             // ---- E3: y1 = relu(fc1([x + h1 + h2, a3])) -- :196-198
             ok = mbar_wait(bar0 + (B_ACC + C_F1) * 8, (ph >> C_F1) & 1u, p.status, 22);
@@ -570,12 +590,17 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             TICK(11);
             // ---- sampling (:210-216): warp w < FPC takes fold FPC rank + w; softmax + inverse CDF as in the fp32 kernel
             if (warp < FPC) {
+                const int fl = FPC * (int)rank + warp;          // fold within the cluster
+                const int bglob = cfold0 + fl;
+                float uu = 0.f, fx = 0.f;                       // the draw and the forced value are fetched while the logits travel
+                if (lane == 0 && fl < nf) {
+                    uu = p.uniforms ? __ldg(p.uniforms + (size_t)t * p.B + bglob) : philox_u01(p.seed, t, bglob);
+                    if (p.forced_x) fx = __ldg(p.forced_x + (size_t)t * p.B + bglob);
+                }
                 ok = mbar_wait(bar0 + B_LG * 8, (ph >> 6) & 1u, p.status, 26);
                 ph ^= 1u << 6;
                 if (!ok) break;
                 TICK(6);
-                const int fl = FPC * (int)rank + warp;          // fold within the cluster
-                const int bglob = cfold0 + fl;
                 const float *lg = reinterpret_cast<const float *>(smem + SM_SAMP) + ((lane >> 2) * FPC + warp) * UPC + (lane & 3) * 16;
                 float v[16];
 #pragma unroll
@@ -596,7 +621,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                 float run = 0.f;
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    run += expf(v[j] - m);
+                    run += __expf(v[j] - m);
                     v[j] = run;
                 }
                 float incl = run;
@@ -607,11 +632,6 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                 }
                 const float excl = incl - run;
                 const float total = __shfl_sync(0xffffffffu, incl, 31);
-                float uu = 0.f, fx = 0.f;
-                if (lane == 0 && fl < nf) {
-                    uu = p.uniforms ? p.uniforms[(size_t)t * p.B + bglob] : philox_u01(p.seed, t, bglob);
-                    if (p.forced_x) fx = p.forced_x[(size_t)t * p.B + bglob];
-                }
                 uu = __shfl_sync(0xffffffffu, uu, 0);
                 fx = __shfl_sync(0xffffffffu, fx, 0);
                 const float thr = uu * total;

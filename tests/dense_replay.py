@@ -13,7 +13,7 @@ SEG = np.dtype([("off16", "<u2"), ("rows", "<u2"), ("nk", "<u2"), ("bsrc16", "<u
 BUNDLE = np.dtype([("bytes", "<u4"), ("src_off", "<u4"), ("nseg", "<u2"), ("wait", "<u2"), ("commit", "<u2"), ("pad", "<u2"),
                    ("seg", SEG, (4,))])
 W_COND = 5
-C_G2, C_F1, C_F2, C_F3, C_G1 = 1, 2, 3, 4, 5
+C_G2, C_F1, C_F2, C_F3, C_G1, C_H2RD = 1, 2, 3, 4, 5, 6
 D_G1_T0, D_G1_1H, D_G1_1I, D_G2_T0, D_G2_1H, D_G2_1I, D_F1, D_F2, D_F3 = 0, 32, 64, 96, 128, 160, 192, 224, 256
 (B1R, U1R, B1Z, U1Z, B1NI, U1N, B1NH, B2R, U2R, B2Z, U2Z, B2NI, U2N, B2NH, B3, U3, B4, B5) = range(18)
 
@@ -122,7 +122,7 @@ class DenseReplay:
                                 acc[rank][col] = np.full((128, B), np.nan)     # uninitialised tensor memory
                             acc[rank][col][:rows] += prod
                 cm = int(bd["commit"])
-                if pre or cm == 0 or cm == C_G1:
+                if pre or cm in (0, C_G1, C_H2RD):
                     continue
                 for rank in range(CL):
                     sl = slice(UPC * rank, UPC * rank + UPC)

@@ -41,7 +41,7 @@ def test_dense_program_shape():
     firsts = sorted(int(s["dcol"]) for bd in r.table for s in bd["seg"][:int(bd["nseg"])] if int(s["first"]))
     assert firsts == [0, 32, 64, 96, 128, 160, 192, 224, 256]
     commits = [int(bd["commit"]) for bd in r.table if int(bd["commit"])]
-    assert commits == [1, 2, 3, 4, 5]
+    assert commits == [1, 2, 3, 4, 5, 6]
 
 
 def test_dense_stream_reproduces_oracle_logits_with_exact_activations():
