@@ -96,7 +96,7 @@ struct DParams {
     int fold0, nfolds, per;        // this launch: folds [fold0, fold0 + nfolds), `per` per cluster
     long long *prof;               // optional [CTAs][PROF_N] cycle counters (development), else nullptr
 };
-constexpr int PROF_N = 32;
+constexpr int PROF_N = 192;       // 0-31 counters, 32.. per-bundle trace of step 10: {wait done, ring slot full, MMAs issued} cycles since the step began
 // profile slots: MMA thread 0-4 wait H1/H2/Y1/Y2/COND, 5 wait ring full, 6 issue, 7 total | epilogue (thread 0) 8-12 wait
 // G1/G2/F1/F2/F3, 13 wait x, 14 wait logits, 15-19 stages E1..E5, 20 sampling, 21 conditioning, 22 total | producer 0: 24 wait empty, 25 total
 
@@ -423,7 +423,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             unsigned ph_full = 0, ph_wait = 0;                  // phase bits: ring slots / wait events
             long long gb = 0;
             bool ok = true;
-            long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_step = 0;
             const long long t_begin = clock64();
             for (int t = -1; t < S && ok; ++t) {
                 const bool pre = t < 0;
@@ -447,30 +447,43 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t slot_base = sb + SM_RING + slot * SLOT;
-                    for (int s = 0; s < bd.nseg; ++s) {
-                        const Seg sg = bd.seg[s];
-                        const uint32_t rows = sg.rows, d = tmem + sg.dcol;
-                        uint32_t a_lo = smem_desc_lo(slot_base + (uint32_t)sg.off16 * 16, rows * 16);
-                        uint32_t b_lo = smem_desc_lo(sb + SM_IMG + (uint32_t)sg.bsrc16 * 16, CHUNK_B);
-                        const uint32_t a_inc = rows * 2;                      // one k-step = 2 chunks of rows x 16 B, in 16-byte units
-                        constexpr uint32_t b_inc = 2 * CHUNK_B / 16;
-                        if (leader) tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, sg.first ? 0u : 1u);
-                        const int nk = sg.nk;
+                    // one elected lane issues the whole bundle: inside an elect.sync region the compiler keeps descriptors and
+                    // loop state in uniform registers (a plain `lane == 0` test costs a register->uniform move per operand per MMA)
+                    if (elect_one()) {
+                        const int nseg = bd.nseg;
+                        for (int s = 0; s < nseg; ++s) {
+                            const Seg sg = bd.seg[s];
+                            const uint32_t rows = sg.rows, d = tmem + sg.dcol;
+                            uint32_t a_lo = smem_desc_lo(slot_base + (uint32_t)sg.off16 * 16, rows * 16);
+                            uint32_t b_lo = smem_desc_lo(sb + SM_IMG + (uint32_t)sg.bsrc16 * 16, CHUNK_B);
+                            const uint32_t a_inc = rows * 2;                  // one k-step = 2 chunks of rows x 16 B, in 16-byte units
+                            constexpr uint32_t b_inc = 2 * CHUNK_B / 16;
+                            tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, sg.first ? 0u : 1u);
+                            const int nk = sg.nk;
 #pragma unroll 4
-                        for (int k = 1; k < nk; ++k) {
-                            a_lo += a_inc;
-                            b_lo += b_inc;
-                            if (leader) tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, 1u);
+                            for (int k = 1; k < nk; ++k) {
+                                a_lo += a_inc;
+                                b_lo += b_inc;
+                                tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, 1u);
+                            }
                         }
-                    }
-                    const int c = bd.commit;
-                    if (leader) {
+                        const int c = bd.commit;
                         tc_commit(bar0 + (B_EMPTY + slot) * 8);
                         if (c == C_H2RD) tc_commit(bar0 + B_H2RD * 8);
                         else if (c != C_NONE && (c == C_G1 || !pre)) tc_commit(bar0 + (B_ACC + (c == C_G1 ? 0 : c)) * 8);
                     }
                     __syncwarp();
-                    if (PROF) pf[6] += clock64() - t2;
+                    if (PROF) {
+                        const long long t3 = clock64();
+                        pf[6] += t3 - t2;
+                        if (t == 10 && p.prof && leader) {
+                            if (b == 0) t_step = t1;
+                            long long *tr = p.prof + (size_t)blockIdx.x * PROF_N + 32 + b * 4;
+                            tr[0] = t1 - t_step;
+                            tr[1] = t2 - t_step;
+                            tr[2] = t3 - t_step;
+                        }
+                    }
                 }
             }
             if (leader) tc_commit(bar0 + B_DONE * 8);

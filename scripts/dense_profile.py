@@ -15,6 +15,7 @@ NAMES = {0: "mma wait H1", 1: "mma wait H2", 2: "mma wait Y1", 3: "mma wait Y2",
 
 
 def main():
+    global out
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
     S = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
     sd = synth.make_state("RAW", "ref", 0)
@@ -29,15 +30,22 @@ def main():
     eng = m._engine(torch.device("cuda", 0))
     _lib.check(eng.lib.wrnn_set_profiling(eng.handle, 1))
     r = run_folds(m, mels, aux, None, seed=3)
-    n = eng.info().ctas * 32
+    n = eng.info().ctas * 192
     out = np.zeros(n, dtype=np.int64)
     _lib.check(eng.lib.wrnn_get_stage_cycles(eng.handle, out.ctypes.data, n))
-    out = out.reshape(-1, 32)
+    out = out.reshape(-1, 192)
     used = min(((B + 31) // 32) * 8, out.shape[0])
     print("co-resident clusters:", eng.info().ctas // 8, "launches", eng.info().launches)
     print("B=%d S=%d kernel %.2f ms = %.2f us/step; cycles per step, CTA 0 | mean over %d CTAs" % (B, S, r["ms"], 1e3 * r["ms"] / S, used))
     for i in sorted(NAMES):
         print("  %-22s %9.0f | %9.0f" % (NAMES[i], out[0, i] / S, out[:used, i].mean() / S))
+
+
+    print("bundle trace of step 10, CTA 0 (cycles since the first bundle's wait began): wait-done, slot-full, issued")
+    tr = out[0, 32:32 + 4 * 40].reshape(40, 4)
+    for b in range(40):
+        if tr[b, 2]:
+            print("  bundle %2d: %6d %6d %6d" % (b, tr[b, 0], tr[b, 1], tr[b, 2]))
 
 
 if __name__ == "__main__":
