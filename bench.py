@@ -213,7 +213,7 @@ def dense_regime(args, dev, state, pk):
                        "frac": tf / pk["bf16_tflops"], "traffic": None,
                        "note": "algorithmic FLOPs (8.14 MFLOP per fold-step); every tcgen05.mma is M=128 x N=32 x K=16 and is paced by "
                                "its shared-memory operand reads (40 clk measured, scripts/umma_rate.cu), the step by the shared-memory "
-                               "port (weights cross it twice: TMA fill + MMA read) and the cluster exchange (DESIGN.md 10)"}
+                               "port (weights cross it twice: TMA fill + MMA read) and the cluster exchange (DESIGN.md 9)"}
     return out
 
 
