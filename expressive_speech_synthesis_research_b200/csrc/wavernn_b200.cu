@@ -423,7 +423,9 @@ static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
     gemm_f64(w->r2_wih, RA, 3 * R, R, bI, 1, c2);
     gemm_f64(w->fc1_w, RA, R, R, bI, 1, c3);
 
-    auto rowT0 = [](int rank, int m) { return m < UPC ? UPC * rank + m : R + UPC * rank + (m - UPC); };   // r rows, then z rows
+    // tile 0: accumulator lane m = 32 q + j holds r (j < 16) or z (j >= 16) of unit 16 q + j % 16, so that a unit's r shares its lane
+    // with the unit's rows of the 64-row tiles (M = 64: row i -> lane 32 (i / 16) + i % 16) and its z sits 16 lanes above
+    auto rowT0 = [](int rank, int m) { return ((m & 31) < 16 ? 0 : R) + UPC * rank + 16 * (m >> 5) + (m & 15); };
     auto rowN = [](int rank, int m) { return 2 * R + UPC * rank + m; };
     auto unit = [](int rank, int m) { return UPC * rank + m; };
     auto img = [](int i, int chunk) { return i * IMG_B + chunk * CHUNK_B; };

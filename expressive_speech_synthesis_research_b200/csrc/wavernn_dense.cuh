@@ -69,7 +69,7 @@ struct Bundle {
 constexpr int SM_RING = 0;
 constexpr int SM_IMG = SM_RING + NSLOT * SLOT;                 // 4 activation images, then the conditioning image
 constexpr int SM_COND = SM_IMG + 4 * IMG_B;
-constexpr int SM_SCRATCH = SM_COND + COND_B;                   // [BC][UPC] fp32: candidate state n (E1/E2), logits staging (E5)
+constexpr int SM_SCRATCH = SM_COND + COND_B;                   // [BC][UPC] fp32: logits staging (E5)
 constexpr int SM_SAMP = SM_SCRATCH + BC * UPC * 4;             // [CL src][FPC][UPC] fp32 logits of this CTA's folds
 constexpr int SM_X = SM_SAMP + CL * FPC * UPC * 4;             // [BC] fp32 fed-back sample
 constexpr int SM_FOLD = SM_X + BC * 4;                         // [2][BC] int32 first row / limit row
@@ -175,8 +175,11 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 // LBO = byte distance between the two core matrices of a k-step along K, SBO = between 8-row groups (128 B here)
 __device__ __forceinline__ uint32_t smem_desc_lo(uint32_t addr, uint32_t lbo_bytes) { return ((addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
 constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);       // SBO = 128 B | descriptor version 1 (Blackwell)
-// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = BC
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BC >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor: D fp32, A/B bf16, both K-major, N = BC; M = 128 for the [r | z] tiles, M = 64 for the 64-row tiles
+// (an M = 64 product reads half the A bytes: 24 instead of 40 cycles, scripts/umma_rate.cu).  Accumulator lanes:
+// M = 128: row i -> lane i;  M = 64: row i -> lane 32 (i / 16) + i % 16  (scripts/umma_m64.cu)
+constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BC >> 3) << 17);
+constexpr uint32_t IDESC128 = IDESC_BASE | ((uint32_t)(128 >> 4) << 24), IDESC64 = IDESC_BASE | ((uint32_t)(64 >> 4) << 24);
 
 // one MUFU per gate (the GRU epilogues are MUFU-bound): tanh.approx has 2^-11 relative error, well inside the bf16 rounding
 // (2^-9) that every activation of this path goes through anyway
@@ -253,68 +256,53 @@ __device__ __forceinline__ void send_slice(uint32_t smem_base, int img, uint32_t
     __syncwarp();
 }
 
-// GRU epilogue of one layer (torch.nn.GRUCell, fatchord_version.py:190,194): lanes 0-63 of the accumulators hold
-// r (tile 0), W_hn.h (tile 1h) and W_in.x (tile 1i) of the CTA's units, lanes 64-127 of tile 0 hold z.
-// R threads (quads 0,1) publish n = tanh(i_n + r * h_n) through shared memory; Z threads (quads 2,3) own the fp32
-// state, finish h' = n + z (h - n) and write its bf16 image.
+// GRU epilogue of one layer (torch.nn.GRUCell, fatchord_version.py:190,194).  Accumulator lanes of warp quad q:
+//   lanes 0-15  ("r lanes"): unit 16 q + l:      r (tile 0, M = 128), W_hn.h and W_in.x (64-row tiles, M = 64)
+//   lanes 16-31 ("z lanes"): unit 16 q + l - 16: z (tile 0); they own the fp32 state of the unit
+// Both kinds run the same instruction stream: gate = sigmoid(acc0 + ...) is r or z by lane, the candidate n = tanh(i_n + r h_n)
+// is meaningful in r lanes and handed to the unit's z lane with one shuffle, which finishes h' = n + z (h - n) and writes bf16.
 __device__ __forceinline__ void gru_epilogue(uint32_t tmem, int col_t0, int col_1h, int col_1i, uint8_t *smem, int img, uint32_t rank, int warp, int lane,
-                                             float b_r, float u_r, float b_ni, float u_n, float b_nh, float b_z, float u_z, float (&hprev)[16])
+                                             float b_g, float u_g, float b_ni, float u_n, float b_nh, float (&hprev)[16])
 {
     const int q = warp & 3, hf = warp >> 2;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const float *xs = reinterpret_cast<const float *>(smem + SM_X);
-    float *scratch = reinterpret_cast<float *>(smem + SM_SCRATCH);
-    float zz[16];
-    if (q < 2) {
-        const int u = q * 32 + lane;
-        float r[16], nh[16], ni[16];
-        tc_ld16(tmem + lane_base + col_t0 + 16 * hf, r);
-        tc_ld16(tmem + lane_base + col_1h + 16 * hf, nh);
-        tc_ld16(tmem + lane_base + col_1i + 16 * hf, ni);
-        tc_ld_wait();
+    float g0[16], nh[16], ni[16];
+    tc_ld16(tmem + lane_base + col_t0 + 16 * hf, g0);
+    tc_ld16(tmem + lane_base + col_1h + 16 * hf, nh);
+    tc_ld16(tmem + lane_base + col_1i + 16 * hf, ni);
+    tc_ld_wait();
+    const bool zlane = lane >= 16;
+    const int u = 16 * q + (lane & 15);
+    uint8_t *dst = smem + SM_IMG + img * IMG_B + (rank * (UPC / 8) + (u >> 3)) * CHUNK_B + (u & 7) * 2;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int f = 16 * hf + j;
-            const float x = xs[f];
-            const float rr = sigmoid_(r[j] + fmaf(x, u_r, b_r));
-            const float nn = tanh_(ni[j] + fmaf(x, u_n, b_ni) + rr * (nh[j] + b_nh));
-            scratch[f * UPC + u] = nn;
-        }
-    } else {
-        float z[16];
-        tc_ld16(tmem + lane_base + col_t0 + 16 * hf, z);
-        tc_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) zz[j] = sigmoid_(z[j] + fmaf(xs[16 * hf + j], u_z, b_z));
-    }
-    tc_fence_before();
-    epi_sync();
-    if (q >= 2) {
-        const int u = (q - 2) * 32 + lane;
-        uint8_t *dst = smem + SM_IMG + img * IMG_B + (rank * (UPC / 8) + (u >> 3)) * CHUNK_B + (u & 7) * 2;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int f = 16 * hf + j;
-            const float nn = scratch[f * UPC + u];
-            const float h = fmaf(zz[j], hprev[j] - nn, nn);
+    for (int j = 0; j < 16; ++j) {
+        const int f = 16 * hf + j;
+        const float x = xs[f];
+        const float gate = sigmoid_(g0[j] + fmaf(x, u_g, b_g));
+        float nn = tanh_(ni[j] + fmaf(x, u_n, b_ni) + gate * (nh[j] + b_nh));
+        nn = __shfl_sync(0xffffffffu, nn, lane & 15);
+        if (zlane) {
+            const float h = fmaf(gate, hprev[j] - nn, nn);
             hprev[j] = h;
             *reinterpret_cast<__nv_bfloat16 *>(dst + f * 16) = __float2bfloat16_rn(h);
         }
-        fence_async_smem();
     }
+    fence_async_smem();
+    tc_fence_before();
     epi_sync();
 }
 
-// fc epilogue: rows 0-63 (quads 0,1) hold the CTA's units; relu(acc + b + x u) -> bf16 image
+// fc epilogue: 64-row tile (M = 64): unit 16 q + l in lanes 0-15 of every quad; relu(acc + b + x u) -> bf16 image
 __device__ __forceinline__ void fc_epilogue(uint32_t tmem, int col, uint8_t *smem, int img, uint32_t rank, int warp, int lane, float b, float ux)
 {
     const int q = warp & 3, hf = warp >> 2;
-    if (q < 2) {
-        const int u = q * 32 + lane;
-        const float *xs = reinterpret_cast<const float *>(smem + SM_X);
-        float a[16];
-        tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + col + 16 * hf, a);
-        tc_ld_wait();
+    const int u = 16 * q + (lane & 15);
+    const float *xs = reinterpret_cast<const float *>(smem + SM_X);
+    float a[16];
+    tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + col + 16 * hf, a);
+    tc_ld_wait();
+    if (lane < 16) {
         uint8_t *dst = smem + SM_IMG + img * IMG_B + (rank * (UPC / 8) + (u >> 3)) * CHUNK_B + (u & 7) * 2;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -322,8 +310,8 @@ __device__ __forceinline__ void fc_epilogue(uint32_t tmem, int col, uint8_t *sme
             const float y = fmaxf(a[j] + fmaf(xs[f], ux, b), 0.0f);
             *reinterpret_cast<__nv_bfloat16 *>(dst + f * 16) = __float2bfloat16_rn(y);
         }
-        fence_async_smem();
     }
+    fence_async_smem();
     tc_fence_before();
     epi_sync();
 }
@@ -454,6 +442,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                         for (int s = 0; s < nseg; ++s) {
                             const Seg sg = bd.seg[s];
                             const uint32_t rows = sg.rows, d = tmem + sg.dcol;
+                            const uint32_t IDESC = rows == 64 ? IDESC64 : IDESC128;
                             uint32_t a_lo = smem_desc_lo(slot_base + (uint32_t)sg.off16 * 16, rows * 16);
                             uint32_t b_lo = smem_desc_lo(sb + SM_IMG + (uint32_t)sg.bsrc16 * 16, CHUNK_B);
                             const uint32_t a_inc = rows * 2;                  // one k-step = 2 chunks of rows x 16 B, in 16-byte units
@@ -497,10 +486,11 @@ __device__ __forceinline__ void dense_body(const DParams &p)
         // ===== epilogue warps =====
         const int q = warp & 3;
         const float *sv = p.sv + (size_t)rank * NSV * UPC;
-        const int u = (q & 1) * 32 + lane;                      // unit of this thread's accumulator lane (R: q 0,1; Z: q 2,3)
-        const float b1r = sv[DV_B1R * UPC + u], u1r = sv[DV_U1R * UPC + u], b1z = sv[DV_B1Z * UPC + u], u1z = sv[DV_U1Z * UPC + u];
+        const int u = 16 * q + (lane & 15);                     // unit of this thread's accumulator lane
+        const bool zl = lane >= 16;                             // z lane (owns the state) or r lane
+        const float b1g = sv[(zl ? DV_B1Z : DV_B1R) * UPC + u], u1g = sv[(zl ? DV_U1Z : DV_U1R) * UPC + u];
         const float b1ni = sv[DV_B1NI * UPC + u], u1n = sv[DV_U1N * UPC + u], b1nh = sv[DV_B1NH * UPC + u];
-        const float b2r = sv[DV_B2R * UPC + u], u2r = sv[DV_U2R * UPC + u], b2z = sv[DV_B2Z * UPC + u], u2z = sv[DV_U2Z * UPC + u];
+        const float b2g = sv[(zl ? DV_B2Z : DV_B2R) * UPC + u], u2g = sv[(zl ? DV_U2Z : DV_U2R) * UPC + u];
         const float b2ni = sv[DV_B2NI * UPC + u], u2n = sv[DV_U2N * UPC + u], b2nh = sv[DV_B2NH * UPC + u];
         const float b3 = sv[DV_B3 * UPC + u], u3 = sv[DV_U3 * UPC + u], b4 = sv[DV_B4 * UPC + u], b5 = sv[DV_B5 * UPC + u];
         float h1[16], h2[16];
@@ -534,7 +524,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             }
             TICK(5);
             tc_fence_after();
-            gru_epilogue(tmem, D_G1_T0, D_G1_1H, D_G1_1I, smem, IMG_H1, rank, warp, lane, b1r, u1r, b1ni, u1n, b1nh, b1z, u1z, h1);
+            gru_epilogue(tmem, D_G1_T0, D_G1_1H, D_G1_1I, smem, IMG_H1, rank, warp, lane, b1g, u1g, b1ni, u1n, b1nh, h1);
             if (warp == 0) send_slice(sb, IMG_H1, rank, lane);
             TICK(7);
             // conditioning of step t+1 -> image (all MMAs that read the image of step t completed before the G1 commit)
@@ -550,7 +540,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             if (!ok) break;
             TICK(1);
             tc_fence_after();
-            gru_epilogue(tmem, D_G2_T0, D_G2_1H, D_G2_1I, smem, IMG_H2, rank, warp, lane, b2r, u2r, b2ni, u2n, b2nh, b2z, u2z, h2);
+            gru_epilogue(tmem, D_G2_T0, D_G2_1H, D_G2_1I, smem, IMG_H2, rank, warp, lane, b2g, u2g, b2ni, u2n, b2nh, h2);
             if (warp == 0) {                                    // every CTA has finished reading the h2(t-1) image (relay warp)
                 ok = mbar_wait(bar0 + (B_H2OK + (t & 1)) * 8, (unsigned)((t >> 1) & 1), p.status, 27);
                 send_slice(sb, IMG_H2, rank, lane);
@@ -580,14 +570,16 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             if (!ok) break;
             TICK(4);
             tc_fence_after();
-            if (q < 2) {
+            {
                 const int hf = warp >> 2;
                 float a[16];
                 tc_ld16(tmem + ((uint32_t)(q * 32) << 16) + D_F3 + 16 * hf, a);
                 tc_ld_wait();
                 float *stage = reinterpret_cast<float *>(smem + SM_SCRATCH);
+                if (lane < 16) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) stage[(16 * hf + j) * UPC + u] = a[j] + b5;
+                    for (int j = 0; j < 16; ++j) stage[(16 * hf + j) * UPC + u] = a[j] + b5;
+                }
                 fence_async_smem();
             }
             tc_fence_before();

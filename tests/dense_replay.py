@@ -85,9 +85,14 @@ class DenseReplay:
                 c[80:] = aux[:, step].T
             return rnd(c)
 
+        # accumulator lanes as the kernel reads them: tile 0 (M = 128, row = lane) holds r of unit 16q+j in lane 32q+j and its z
+        # 16 lanes above; a 64-row tile (M = 64) leaves row i in lane 32 (i // 16) + i % 16, modelled here as plain row i
+        uu = np.arange(UPC)
+        r_lane = 32 * (uu // 16) + uu % 16
+
         def gru(rank, t0, c1h, c1i, sv, br, ur, bz, uz, bni, un, bnh, hprev):
             a0 = acc[rank][t0]
-            r, z = a0[:UPC], a0[UPC:2 * UPC]
+            r, z = a0[r_lane], a0[r_lane + 16]
             nh, ni = acc[rank][c1h][:UPC], acc[rank][c1i][:UPC]
             col = lambda i: sv[i][:, None]
             rr = sig(r + col(br) + x * col(ur))
