@@ -13,14 +13,14 @@ __device__ __forceinline__ bool try_wait(uint32_t bar, unsigned parity)
 }
 // mode 0: no swizzle, LBO = rows*16, SBO = 128, k-step advance 2*rows*16
 // mode 1: 128B swizzle, rows of 128 B (64 k), SBO = 1024, k-step advance 32 B, 4 k-steps per 64-k block then + rows*128
-__global__ void __launch_bounds__(384, 1) rate_kernel(int mode, int M, int N, int rowsA, int nmma, long long *out, const uint8_t *gsrc, int stream, int commit_every, int spin)
+__global__ void __launch_bounds__(128, 1) rate_kernel(int mode, int M, int N, int rowsA, int nmma, long long *out, const uint8_t *gsrc, int stream, int commit_every)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar, sbar[2], cbar;
     __shared__ uint32_t tmem_s;
     __shared__ volatile int stop;
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < 200 * 1024 / 4; i += 384) ((uint32_t *)smem)[i] = 0x3c003c00u;
+    for (int i = tid; i < 200 * 1024 / 4; i += 128) ((uint32_t *)smem)[i] = 0x3c003c00u;
     if (tid == 0) { stop = 0; asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&sbar[0]))); asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&sbar[1]))); asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&cbar)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (warp == 0) {
@@ -55,8 +55,12 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(int mode, int M, int N, in
             if (pred)
                 asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
                              "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem), "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(i > 0 ? 1u : 0u));
-            if (commit_every && (i & (commit_every - 1)) == commit_every - 1 && pred)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&cbar)) : "memory");
+            if (commit_every && (i & (commit_every - 1)) == commit_every - 1) {
+                if (pred) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&cbar)) : "memory");
+                if (stream & 2) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (stream & 4) { while (!try_wait(s32(&sbar[1]), 1)) {} }
+                if (stream & 8) __syncwarp();
+            }
             if ((i & 3) == 3) {
                 if (mode == 0) { a_lo = a_lo0 + ((i >> 2) & 3) * 4 * a_inc; b_lo = b_lo0; }
                 else { a_lo = a_lo0 + (((i >> 2) & 3) * rowsA * 128 >> 4); b_lo = b_lo0; }
@@ -82,25 +86,6 @@ __global__ void __launch_bounds__(384, 1) rate_kernel(int mode, int M, int N, in
         }
         out[2 + pw] = bytes;
     }
-    if (warp >= 4 && spin) {
-        float acc = 0.f;
-        unsigned n = 0;
-        while (!stop) {
-            if (spin == 1) { if (try_wait(s32(&sbar[0]) + 0, 1u ^ 0u) && n == 0xffffffffu) acc += 1.f; }        // mbarrier polling (all lanes)
-            else if (spin == 2) { acc += ((volatile float *)smem)[(tid * 4 + (n & 1023) * 32) & 0xffff]; }             // LDS traffic
-            else if (spin == 3) {                                                                                      // tensor-memory loads
-                uint32_t v0, v1, v2, v3;
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 64));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                acc += __uint_as_float(v0 ^ v1 ^ v2 ^ v3);
-            }
-            else if (spin == 4) { ((volatile float *)smem)[150 * 256 + tid] = acc; asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }   // generic store + proxy fence
-            else if (spin == 5) { ((volatile float *)smem)[150 * 256 + tid] = acc; __threadfence_block(); }
-            else if (spin == 6) { if ((n & 63) == 0) { ((volatile float *)smem)[150 * 256 + tid] = acc; asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); } else { acc += __sinf(acc + n); } }
-            ++n;
-        }
-        if (acc == 123.456f) out[3] = n;
-    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
@@ -111,17 +96,17 @@ int main()
     uint8_t *g;
     CK(cudaMalloc(&d, 32));
     CK(cudaMalloc(&g, 200 * 32768));
-    CK(cudaMemset(g, 0x3c, 200 * 32768));
     CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int nmma = 4000;
-    for (int spin = 0; spin < 7; ++spin)
-        for (int stream = 0; stream < 2; ++stream) {
+    const char *names[] = {"commit only", "commit + tcgen05.fence::after_thread_sync", "commit + try_wait on a completed mbarrier", "commit + fence + try_wait", "commit + __syncwarp", "all"};
+    const int flags[] = {0, 2, 4, 6, 8, 14};
+    for (int v = 0; v < 6; ++v)
+        for (int ce : {4, 8, 16}) {
             CK(cudaMemset(d, 0, 32));
-            rate_kernel<<<1, 384, 200 * 1024>>>(0, 128, 32, 128, nmma, d, g, stream, 8, spin);
+            rate_kernel<<<1, 128, 200 * 1024>>>(0, 128, 32, 128, nmma, d, g, flags[v], ce);
             CK(cudaDeviceSynchronize());
             CK(cudaMemcpy(h, d, 32, cudaMemcpyDeviceToHost));
-            printf("M=128 N=32, TMA streaming %s, 8 extra warps %s: %.1f clk/mma\n", stream ? "ON " : "off",
-                   spin == 0 ? "idle" : spin == 1 ? "polling an mbarrier" : spin == 2 ? "reading shared memory" : spin == 3 ? "reading tensor memory" : spin == 4 ? "st.shared + fence.proxy.async in a tight loop" : spin == 5 ? "st.shared + membar.cta in a tight loop" : "fence.proxy.async every 64 iterations of math", (double)h[1] / nmma);
+            printf("every %2d MMAs: %-45s %.1f clk/mma\n", ce, names[v], (double)h[1] / nmma);
         }
     return 0;
 }
