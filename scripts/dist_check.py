@@ -18,11 +18,13 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for mode, T, target, overlap in (("RAW", 60, 1000, 100), ("MOL", 45, 700, 50), ("RAW", 30, 2000, 200)):
+    for mode, T, target, overlap, precision in (("RAW", 60, 1000, 100, "fp32"), ("MOL", 45, 700, 50, "fp32"), ("RAW", 30, 2000, 200, "fp32"),
+                                                ("RAW", 400, 1000, 100, "bf16-dense")):
         sd = synth.make_state(mode, "ref", 0)
         m = WaveRNN(**synth.model_kwargs(mode, "ref"))
         m.load_state_dict(sd)
         m.cuda()
+        m.precision = precision                       # bf16-dense: 73 folds, two or three clusters per rank (tcgen05 kernel)
         mel = synth.make_mel(T, seed=3)
         L = T * 200
         B = (L - overlap) // (target + overlap)
@@ -35,7 +37,7 @@ def main():
             want = m.generate(mel, True, target, overlap, True, uniforms=U)
             same = wav.shape == want.shape and np.array_equal(wav, want)
             ok &= bool(same)
-            print("sharded %s: %d folds over %d ranks, wave_len %d, bit-identical to single GPU: %s" % (mode, B, world, want.size, same), flush=True)
+            print("sharded %s %s: %d folds over %d ranks, wave_len %d, bit-identical to single GPU: %s" % (mode, precision, B, world, want.size, same), flush=True)
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1

@@ -18,4 +18,4 @@ def test_sharded_generation_matches_single_gpu_over_nccl():
            "--master-port", "29533", os.path.join(ROOT, "scripts", "dist_check.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert res.stdout.count("bit-identical to single GPU: True") == 3, res.stdout[-2000:]
+    assert res.stdout.count("bit-identical to single GPU: True") == 4, res.stdout[-2000:]
