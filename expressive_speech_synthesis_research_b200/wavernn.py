@@ -360,37 +360,75 @@ class WaveRNN(nn.Module):
                 with torch.cuda.device(device):
                     if self.upsample.resnet.conv_in.weight.device != device:
                         self.to(device)
-                    conds, starts, limits, meta, base = [], [], [], [], 0
                     S = target + 2 * overlap
+                    # plan: fold counts from the mel lengths alone (fold_with_overlap index arithmetic, :298-309)
+                    plan = []
                     for mel in mel_list:
-                        mel = mel.to(device=device, dtype=torch.float32)
                         wave_len = (mel.size(-1) - 1) * self.hop_length
                         if wave_len < 20 * self.hop_length:
                             raise ValueError("utterance shorter than 21 frames")
-                        m_up, aux = self.conditioning(mel)
-                        L = m_up.size(0)
+                        L = mel.size(-1) * self.hop_length                                   # rows the conditioning network returns
                         B, _ = _lib.fold_index(L, target, overlap)
                         if B <= 0:
                             raise RuntimeError("utterance yields no folds")
-                        starts.append(base + np.arange(B, dtype=np.int64) * (target + overlap))
-                        limits.append(np.full(B, base + L, dtype=np.int64))
-                        meta.append((B, wave_len))
-                        conds.append((m_up, aux))
-                        base += L
-                    m_all = torch.cat([c[0] for c in conds]).contiguous()
-                    a_all = torch.cat([c[1] for c in conds]).contiguous()
-                    res = self._run_folds(eng, device, m_all, a_all, np.concatenate(starts), np.concatenate(limits), S,
-                                          uniforms, seed, None, False)
+                        plan.append((B, L, wave_len))
+                    total_folds = sum(p[0] for p in plan)
+                    if uniforms is not None:
+                        uniforms = torch.as_tensor(uniforms)
+                        if uniforms.size(1) != total_folds:
+                            raise ValueError("uniforms must have %d fold columns, got %d" % (total_folds, uniforms.size(1)))
+                    # Utterances are pooled in CHUNKS of about two waves of the step-loop kernel: the upsampled conditioning of a chunk
+                    # (832 B per sample) is produced, consumed and its memory reused, instead of materialising it for the whole set
+                    # (34 GB for BASELINE.json configs[3]); fold results do not depend on how folds are pooled (tests: pooling /
+                    # chunking / placement invariance), so the waveforms are the ones of the unchunked call.
+                    cap = max(1, int(eng.info().max_folds_per_launch))
+                    goal = cap * max(1, round(960 / cap))
+                    chunks, cur, cur_folds = [], [], 0
+                    for idx, (B, L, wave_len) in enumerate(plan):
+                        if cur and cur_folds + B > goal:
+                            chunks.append(cur)
+                            cur, cur_folds = [], 0
+                        cur.append(idx)
+                        cur_folds += B
+                    if cur:
+                        chunks.append(cur)
                     stream = torch.cuda.current_stream(device).cuda_stream
-                    outs, b0 = [], 0
-                    for B, wave_len in meta:
-                        wav = torch.empty(wave_len, dtype=torch.float64, device=device)
-                        _lib.check(eng.lib.wrnn_xfade_unfold(res["samples"][b0:b0 + B].data_ptr(), B, S, 1, overlap,
-                                                             self.n_classes if mu_law else 0, wave_len,
-                                                             20 * self.hop_length, wav.data_ptr(), ctypes.c_void_p(stream)))
-                        outs.append(wav)
-                        b0 += B
-                    self.last_stats.update(folds=b0, steps=S, kernel_ms=eng.info().last_kernel_ms)
+                    outs, fold0, kernel_ms = [None] * len(plan), 0, 0.0
+                    for ci, chunk in enumerate(chunks):
+                        rows = sum(plan[i][1] for i in chunk)
+                        m_all = torch.empty(rows, self._feat_dims, dtype=torch.float32, device=device)
+                        a_all = torch.empty(rows, 4 * self.aux_dims, dtype=torch.float32, device=device)
+                        starts, limits, base = [], [], 0
+                        for i in chunk:
+                            B, L, _ = plan[i]
+                            m_up, aux = self.conditioning(mel_list[i].to(device=device, dtype=torch.float32))
+                            if m_up.size(0) != L:
+                                raise RuntimeError("conditioning network returned %d rows, expected %d" % (m_up.size(0), L))
+                            m_all[base:base + L].copy_(m_up)
+                            a_all[base:base + L].copy_(aux)
+                            del m_up, aux
+                            starts.append(base + np.arange(B, dtype=np.int64) * (target + overlap))
+                            limits.append(np.full(B, base + L, dtype=np.int64))
+                            base += L
+                        nf = sum(plan[i][0] for i in chunk)
+                        u = None if uniforms is None else uniforms[:, fold0:fold0 + nf].contiguous()
+                        sd = None if seed is None else int(seed) + ci        # in-kernel draws: one Philox stream per chunk
+                        res = self._run_folds(eng, device, m_all, a_all, np.concatenate(starts), np.concatenate(limits), S, u, sd, None, False)
+                        kernel_ms += eng.info().last_kernel_ms
+                        b0 = 0
+                        for i in chunk:
+                            B, _, wave_len = plan[i]
+                            wav = torch.empty(wave_len, dtype=torch.float64, device=device)
+                            _lib.check(eng.lib.wrnn_xfade_unfold(res["samples"][b0:b0 + B].data_ptr(), B, S, 1, overlap,
+                                                                 self.n_classes if mu_law else 0, wave_len,
+                                                                 20 * self.hop_length, wav.data_ptr(), ctypes.c_void_p(stream)))
+                            outs[i] = wav
+                            b0 += B
+                        fold0 += nf
+                        torch.cuda.current_stream(device).synchronize()     # the chunk's buffers are reused by the next one
+                        del m_all, a_all, res
+                    b0 = total_folds
+                    self.last_stats.update(folds=b0, steps=S, kernel_ms=kernel_ms, chunks=len(chunks))
                     return [w.cpu().numpy() for w in outs]
         finally:
             self.train()
