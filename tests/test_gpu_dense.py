@@ -121,3 +121,25 @@ def test_dense_generate_end_to_end_matches_assembly_of_its_own_samples():
     samples = ex["samples"].cpu().numpy()
     want = c_oracle.assemble(samples, True, target, overlap, 512, (T - 1) * hop, hop)
     assert np.abs(wav - want).max() <= H.TOL_MULAW_ABS
+
+
+def test_dense_generate_many_chunks_match_single_utterance_calls():
+    """A sentence set larger than one chunk of generate_many (> 960 pooled folds): every waveform must equal the one
+    generate() returns for that utterance alone with the matching slice of the draws (pooling, chunking and cluster
+    placement do not change a fold)."""
+    from expressive_speech_synthesis_research_b200 import _lib
+    m = dense_model()
+    t, o = 300, 20
+    S = t + 2 * o
+    mels = [synth.make_mel(50 + (7 * i) % 23, seed=60 + i) for i in range(32)]
+    folds = [_lib.fold_index(mm.shape[-1] * 200, t, o)[0] for mm in mels]
+    assert sum(folds) > 960
+    U = synth.make_uniforms(S, sum(folds), "RAW", seed=8)
+    pooled = m.generate_many(mels, t, o, True, uniforms=U)
+    assert m.last_stats["chunks"] >= 2
+    b0 = 0
+    for k, (mm, nb, wav) in enumerate(zip(mels, folds, pooled)):
+        if k % 5 == 0 or k == len(mels) - 1:
+            single = m.generate(mm, True, t, o, True, uniforms=U[:, b0:b0 + nb])
+            assert np.array_equal(single, wav), k
+        b0 += nb
