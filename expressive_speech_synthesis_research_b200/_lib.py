@@ -44,6 +44,7 @@ SYMBOLS = {
     "wrnn_dense_pack_host": (i32, [ctypes.POINTER(Config), ctypes.POINTER(Weights), vp, vp, vp]),
     "wrnn_fold_index": (i32, [i64, i64, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
     "wrnn_generate_folds": (i32, [vp, vp, vp, i64, vp, vp, i32, i32, vp, u64, vp, vp, vp, vp, vp]),
+    "wrnn_generate_folds_frames": (i32, [vp, vp, i64, vp, i64, vp, i32, i32, vp, i32, i32, vp, u64, vp, vp, vp, vp, vp]),
     "wrnn_xfade_unfold": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, vp, vp]),
     "wrnn_xfade_unfold_segment": (i32, [vp, i32, i32, i32, i32, i64, i32, i64, i64, i64, i64, vp, vp]),
     "wrnn_get_info": (i32, [vp, ctypes.POINTER(Info)]),

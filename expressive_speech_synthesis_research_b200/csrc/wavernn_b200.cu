@@ -190,6 +190,7 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
         }
         H_TRY(cudaFuncSetAttribute(wrnn_dense::wavernn_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wrnn_dense::SM_TOTAL));
         H_TRY(cudaFuncSetAttribute(wrnn_dense::wavernn_dense_kernel_prof, cudaFuncAttributeMaxDynamicSharedMemorySize, wrnn_dense::SM_TOTAL));
+        H_TRY(cudaFuncSetAttribute(wrnn_dense::wavernn_dense_kernel_frames, cudaFuncAttributeMaxDynamicSharedMemorySize, wrnn_dense::SM_TOTAL));
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(wrnn_dense::CL * 64);
         lc.blockDim = dim3(wrnn_dense::DTHREADS);
@@ -712,6 +713,57 @@ static void fill_common(wrnn_handle *h, KParams &p)
     p.auxw = 4 * h->cfg.aux_dims;
 }
 
+// dense step loop (csrc/wavernn_dense.cuh): one launch holds every fold; clusters are independent
+static int32_t launch_dense(wrnn_handle *h, wrnn_dense::DParams dp, bool frames, int32_t num_folds, int32_t steps, cudaStream_t st)
+{
+    using namespace wrnn_dense;
+    // clusters are independent (no grid-level synchronisation): one launch holds every fold, the hardware runs the
+    // clusters in waves of h->dense_clusters
+    const int cap = 2048 * BC;
+    for (int b0 = 0; b0 < num_folds; b0 += cap) {
+        const int nb = num_folds - b0 < cap ? num_folds - b0 : cap;
+        // whole waves of co-resident clusters, folds dealt evenly: a cluster's step time hardly depends on its fold count
+        int ncl = (nb + BC - 1) / BC;
+        if (ncl > h->dense_clusters) ncl = (ncl + h->dense_clusters - 1) / h->dense_clusters * h->dense_clusters;
+        if (ncl > nb) ncl = nb;
+        dp.wstream = h->dense_stream;
+        dp.table = h->dense_table;
+        dp.sv = h->dense_sv;
+        dp.status = h->status;
+        dp.stream_bytes = h->dense_stream_bytes;
+        dp.nb = h->dense_nb;
+        dp.B = num_folds;
+        dp.S = steps;
+        dp.fold0 = b0;
+        dp.nfolds = nb;
+        dp.per = (nb + ncl - 1) / ncl;
+        dp.prof = nullptr;
+        if (h->profiling && !frames) {
+            if (!h->dense_prof) CUDA_TRY(cudaMalloc(&h->dense_prof, (size_t)h->dense_clusters * CL * PROF_N * sizeof(long long)));
+            CUDA_TRY(cudaMemsetAsync(h->dense_prof, 0, (size_t)h->dense_clusters * CL * PROF_N * sizeof(long long), st));
+            dp.prof = h->dense_prof;
+        }
+        CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
+        CUDA_TRY(cudaEventRecord(h->ev0, st));
+        if (frames) wavernn_dense_kernel_frames<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
+        else if (dp.prof) wavernn_dense_kernel_prof<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
+        else wavernn_dense_kernel<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(h->ev1, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        h->last_ms += ms;
+        h->launches += 1;
+        h->smem_bytes = SM_TOTAL;
+        int status[4];
+        CUDA_TRY(cudaMemcpy(status, h->status, sizeof status, cudaMemcpyDeviceToHost));
+        h->last_status = status[0];
+        if (status[0] != 0) return fail(WRNN_ERR_TIMEOUT, "dense kernel watchdog fired (wait code %d): a pipeline barrier never completed", status[0]);
+    }
+    return WRNN_OK;
+}
+
 extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const float *aux, int64_t cond_rows,
                                        const int64_t *fold_start, const int64_t *fold_limit,
                                        int32_t num_folds, int32_t steps,
@@ -741,64 +793,20 @@ extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const 
 
     h->last_ms = 0.f;
     if (h->dense) {
-        // every launch keeps as many clusters busy as fit at once; folds are dealt evenly, at most BC per cluster
-        using namespace wrnn_dense;
         if (cond_rows > 0x7fffffffll) return fail(WRNN_ERR_INVALID, "dense path indexes conditioning rows with 32 bits (got %lld rows)", (long long)cond_rows);
-        // clusters are independent (no grid-level synchronisation): one launch holds every fold, the hardware runs the
-        // clusters in waves of h->dense_clusters
-        const int cap = 2048 * BC;
-        for (int b0 = 0; b0 < num_folds; b0 += cap) {
-            const int nb = num_folds - b0 < cap ? num_folds - b0 : cap;
-            // whole waves of co-resident clusters, folds dealt evenly: a cluster's step time hardly depends on its fold count
-            int ncl = (nb + BC - 1) / BC;
-            if (ncl > h->dense_clusters) ncl = (ncl + h->dense_clusters - 1) / h->dense_clusters * h->dense_clusters;
-            if (ncl > nb) ncl = nb;
-            DParams dp;
-            memset(&dp, 0, sizeof dp);
-            dp.wstream = h->dense_stream;
-            dp.table = h->dense_table;
-            dp.sv = h->dense_sv;
-            dp.mels = mels;
-            dp.aux = aux;
-            dp.fold_start = h->fold_dev;
-            dp.fold_limit = h->fold_dev + h->fold_cap;
-            dp.uniforms = uniforms;
-            dp.forced_x = forced_x;
-            dp.logits_out = logits_out;
-            dp.samples_out = samples_out;
-            dp.labels_out = labels_out;
-            dp.seed = seed;
-            dp.status = h->status;
-            dp.stream_bytes = h->dense_stream_bytes;
-            dp.nb = h->dense_nb;
-            dp.B = num_folds;
-            dp.S = steps;
-            dp.fold0 = b0;
-            dp.nfolds = nb;
-            dp.per = (nb + ncl - 1) / ncl;
-            if (h->profiling) {
-                if (!h->dense_prof) CUDA_TRY(cudaMalloc(&h->dense_prof, (size_t)h->dense_clusters * CL * PROF_N * sizeof(long long)));
-                CUDA_TRY(cudaMemsetAsync(h->dense_prof, 0, (size_t)h->dense_clusters * CL * PROF_N * sizeof(long long), st));
-                dp.prof = h->dense_prof;
-            }
-            CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
-            CUDA_TRY(cudaEventRecord(h->ev0, st));
-            if (dp.prof) wavernn_dense_kernel_prof<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
-            else wavernn_dense_kernel<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaEventRecord(h->ev1, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            float ms = 0.f;
-            CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-            h->last_ms += ms;
-            h->launches += 1;
-            h->smem_bytes = SM_TOTAL;
-            int status[4];
-            CUDA_TRY(cudaMemcpy(status, h->status, sizeof status, cudaMemcpyDeviceToHost));
-            h->last_status = status[0];
-            if (status[0] != 0) return fail(WRNN_ERR_TIMEOUT, "dense kernel watchdog fired (wait code %d): a pipeline barrier never completed", status[0]);
-        }
-        return WRNN_OK;
+        wrnn_dense::DParams dp;
+        memset(&dp, 0, sizeof dp);
+        dp.mels = mels;
+        dp.aux = aux;
+        dp.fold_start = h->fold_dev;
+        dp.fold_limit = h->fold_dev + h->fold_cap;
+        dp.uniforms = uniforms;
+        dp.forced_x = forced_x;
+        dp.logits_out = logits_out;
+        dp.samples_out = samples_out;
+        dp.labels_out = labels_out;
+        dp.seed = seed;
+        return launch_dense(h, dp, false, num_folds, steps, st);
     }
     const int max_chunk = MAXG * BT;
     for (int b0 = 0; b0 < num_folds; b0 += max_chunk) {
@@ -830,6 +838,52 @@ extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const 
         if (rc) return rc;
     }
     return WRNN_OK;
+}
+
+extern "C" int32_t wrnn_generate_folds_frames(wrnn_handle *h, const float *mel_frames, int64_t frame_rows, const float *aux_frames, int64_t aux_rows,
+                                              const float *interp, int32_t hop, int32_t pad, const int32_t *fold_geo, int32_t num_folds, int32_t steps,
+                                              const float *uniforms, uint64_t seed, const float *forced_x, float *logits_out,
+                                              float *samples_out, int32_t *labels_out, void *stream)
+{
+    if (!h) return fail(WRNN_ERR_INVALID, "null handle");
+    if (!h->dense) return fail(WRNN_ERR_INVALID, "in-kernel conditioning expansion is implemented by the dense kernel (precision WRNN_PREC_BF16_DENSE)");
+    if (!h->loaded) return fail(WRNN_ERR_STATE, "wrnn_load_weights has not been called");
+    if (!mel_frames || !aux_frames || !interp || !fold_geo || !samples_out) return fail(WRNN_ERR_INVALID, "null pointer argument");
+    if (num_folds <= 0 || steps <= 0 || hop <= 0 || pad < 2) return fail(WRNN_ERR_INVALID, "num_folds (%d), steps (%d), hop (%d) must be positive and pad (%d) >= 2", num_folds, steps, hop, pad);
+    if (((uintptr_t)mel_frames | (uintptr_t)aux_frames) & 15) return fail(WRNN_ERR_INVALID, "frame pointers must be 16-byte aligned");
+    if (frame_rows > 0x7fffffffll / 128 || aux_rows > 0x7fffffffll / 128) return fail(WRNN_ERR_INVALID, "too many frame rows");
+    for (int b = 0; b < num_folds; ++b) {
+        const int32_t *g = fold_geo + 4 * b;
+        // frames touched by the last valid sample: padded mel frame (len - 1 + pad*hop) / hop + 2, aux frame (len - 1) / hop
+        if (g[0] < 0 || g[1] <= 0 || g[2] < 0 || g[3] < 0 || g[2] + (g[1] - 1 + pad * hop) / hop + 2 >= frame_rows || g[3] + (g[1] - 1) / hop >= aux_rows)
+            return fail(WRNN_ERR_INVALID, "fold %d: geometry {%d, %d, %d, %d} outside the frame tensors (%lld, %lld rows)", b, g[0], g[1], g[2], g[3],
+                        (long long)frame_rows, (long long)aux_rows);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (num_folds > h->fold_cap) {
+        cudaFree(h->fold_dev);
+        h->fold_dev = nullptr;
+        CUDA_TRY(cudaMalloc(&h->fold_dev, (size_t)2 * num_folds * sizeof(long long)));
+        h->fold_cap = num_folds;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->fold_dev, fold_geo, (size_t)num_folds * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    h->last_ms = 0.f;
+    wrnn_dense::DParams dp;
+    memset(&dp, 0, sizeof dp);
+    dp.mel_frames = mel_frames;
+    dp.aux_frames = aux_frames;
+    dp.interp = interp;
+    dp.fold_geo = reinterpret_cast<const int *>(h->fold_dev);
+    dp.hop = hop;
+    dp.indent = pad * hop;
+    dp.uniforms = uniforms;
+    dp.forced_x = forced_x;
+    dp.logits_out = logits_out;
+    dp.samples_out = samples_out;
+    dp.labels_out = labels_out;
+    dp.seed = seed;
+    return launch_dense(h, dp, true, num_folds, steps, st);
 }
 
 extern "C" int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *usec_per_exchange)

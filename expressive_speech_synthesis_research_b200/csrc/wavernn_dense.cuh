@@ -72,8 +72,8 @@ constexpr int SM_COND = SM_IMG + 4 * IMG_B;
 constexpr int SM_SCRATCH = SM_COND + COND_B;                   // [BC][UPC] fp32: logits staging (E5)
 constexpr int SM_SAMP = SM_SCRATCH + BC * UPC * 4;             // [CL src][FPC][UPC] fp32 logits of this CTA's folds
 constexpr int SM_X = SM_SAMP + CL * FPC * UPC * 4;             // [BC] fp32 fed-back sample
-constexpr int SM_FOLD = SM_X + BC * 4;                         // [2][BC] int32 first row / limit row
-constexpr int SM_TAB = SM_FOLD + 2 * BC * 4;
+constexpr int SM_FOLD = SM_X + BC * 4;                         // [4][BC] int32 fold geometry (rows mode uses the first two)
+constexpr int SM_TAB = SM_FOLD + 4 * BC * 4;
 constexpr int SM_BAR = SM_TAB + MAXBUNDLE * (int)sizeof(Bundle);
 enum { B_FULL = 0, B_EMPTY = 2, B_ACT = 4, B_LG = 8, B_X = 9, B_COND = 10, B_ACC = 11, B_DONE = 16, B_H2RD = 17, B_H2OK = 18, NBAR = 20 };   // B_H2OK: two barriers, alternating by step
 constexpr int SM_TMEM = SM_BAR + NBAR * 8;
@@ -85,6 +85,13 @@ struct DParams {
     const float *sv;               // [CL][NSV][UPC]
     const float *mels, *aux;       // fp32 [rows][80], [rows][128]  (UpsampleNetwork output, unfolded)
     const long long *fold_start, *fold_limit;
+    // frames mode (wrnn_generate_folds_frames): the conditioning is expanded in the kernel from FRAME-rate tensors
+    const float *mel_frames;       // [frames][80] mel frames of every utterance, zero-padded by `pad` frames on both sides
+    const float *aux_frames;       // [frames][128] MelResNet output at frame rate
+    const float *interp;           // [hop][5]: four composite interpolation weights of the three (repeat, FIR) stages + first-frame offset
+    const int *fold_geo;           // [B][4]: first sample of the fold in its utterance, samples of the utterance, row of the
+                                   // utterance's first (padded) mel frame, row of its first aux frame
+    int hop, indent;               // samples per frame, pad * hop
     const float *uniforms, *forced_x;
     float *logits_out, *samples_out;
     int *labels_out;
@@ -208,9 +215,12 @@ __device__ __forceinline__ float philox_u01(unsigned long long seed, int step, i
 }
 
 // ---- conditioning: item (kc, f) = 8 consecutive conditioning inputs of fold f, fp32 in global, bf16 in the image ----
-struct CondRegs { float4 v[4][2]; };
-__device__ __forceinline__ void cond_load(const DParams &p, const int *fold_row0, const int *fold_lim, int nf, int tid, int step, CondRegs &cr)
+struct CondRegs { uint4 v[4]; };                                // step t+2's items of this thread, already bf16
+__device__ __forceinline__ uint4 cond_pack(const float4 &a, const float4 &b) { return make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w)); }
+// rows mode: the UpsampleNetwork output is materialised ([rows][80], [rows][128]); fold f reads row fold_row0[f] + step
+__device__ __forceinline__ void cond_load(const DParams &p, const int *geo, int nf, int tid, int step, CondRegs &cr)
 {
+    const int *fold_row0 = geo, *fold_lim = geo + BC;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int i = tid + NEPI * j;
@@ -224,8 +234,65 @@ __device__ __forceinline__ void cond_load(const DParams &p, const int *fold_row0
                 b = __ldg(reinterpret_cast<const float4 *>(src) + 1);
             }
         }
-        cr.v[j][0] = a;
-        cr.v[j][1] = b;
+        cr.v[j] = cond_pack(a, b);
+    }
+}
+// frames mode: UpsampleNetwork.forward (fatchord_version.py:79-86) and fold_with_overlap's gather (:311-319) fused into the load.
+//   aux[p]    = resnet_out[p / hop]                                  (Stretch2d of the MelResNet output, :80-82)
+//   mel_up[p] = sum_j w[r][j] * mel_pad[q + s(r) + j],  q = (p + indent) / hop, r = (p + indent) % hop
+// where w / s are the composite response of the three (Stretch2d, Conv2d box filter) stages (:83-85), measured once per model
+// by pushing an impulse through those layers (host, wavernn.py); the crop by `indent` (:85) keeps the zero padding of the
+// intermediate stages out of every retained sample.  Each item keeps (sample, frame, phase) and advances by one sample per call.
+struct CondState { int pos[4], q[4], r[4]; };
+__device__ __forceinline__ void cond_state_init(const DParams &p, const int *geo, int tid, CondState &st)
+{
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = tid + NEPI * j;
+        const int f = i & (BC - 1), kc = i >> 5;
+        const int pos = geo[f];                                 // first sample of the fold
+        const int shifted = kc < 10 ? pos + p.indent : pos;
+        st.pos[j] = pos;
+        st.q[j] = shifted / p.hop;
+        st.r[j] = shifted - st.q[j] * p.hop;
+    }
+}
+__device__ __forceinline__ void cond_load_frames(const DParams &p, const int *geo, int nf, int tid, int step, CondState &st, CondRegs &cr)
+{
+    const int *len = geo + BC, *mel_base = geo + 2 * BC, *aux_base = geo + 3 * BC;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int i = tid + NEPI * j;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (i < COND_CHUNKS * BC) {
+            const int f = i & (BC - 1), kc = i >> 5;
+            if (f < nf && step < p.S && st.pos[j] < len[f]) {
+                if (kc < 10) {
+                    const float *w = p.interp + st.r[j] * 5;
+                    const float w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2), w3 = __ldg(w + 3);
+                    const int first = (int)__ldg(w + 4);
+                    const float4 *src = reinterpret_cast<const float4 *>(p.mel_frames + (size_t)(mel_base[f] + st.q[j] + first) * 80 + kc * 8);
+                    const float4 a0 = __ldg(src), b0 = __ldg(src + 1), a1 = __ldg(src + 20), b1 = __ldg(src + 21);
+                    const float4 a2 = __ldg(src + 40), b2 = __ldg(src + 41), a3 = __ldg(src + 60), b3 = __ldg(src + 61);
+#define WRNN_MIX(c) fmaf(w3, a3.c, fmaf(w2, a2.c, fmaf(w1, a1.c, w0 * a0.c)))
+#define WRNN_MIXB(c) fmaf(w3, b3.c, fmaf(w2, b2.c, fmaf(w1, b1.c, w0 * b0.c)))
+                    a = make_float4(WRNN_MIX(x), WRNN_MIX(y), WRNN_MIX(z), WRNN_MIX(w));
+                    b = make_float4(WRNN_MIXB(x), WRNN_MIXB(y), WRNN_MIXB(z), WRNN_MIXB(w));
+#undef WRNN_MIX
+#undef WRNN_MIXB
+                } else {
+                    const float4 *src = reinterpret_cast<const float4 *>(p.aux_frames + (size_t)(aux_base[f] + st.q[j]) * 128 + (kc - 10) * 8);
+                    a = __ldg(src);
+                    b = __ldg(src + 1);
+                }
+            }
+        }
+        cr.v[j] = cond_pack(a, b);
+        st.pos[j] += 1;
+        if (++st.r[j] == p.hop) {
+            st.r[j] = 0;
+            st.q[j] += 1;
+        }
     }
 }
 __device__ __forceinline__ void cond_store(uint8_t *cond_img, int tid, const CondRegs &cr)
@@ -235,8 +302,7 @@ __device__ __forceinline__ void cond_store(uint8_t *cond_img, int tid, const Con
         const int i = tid + NEPI * j;
         if (i < COND_CHUNKS * BC) {
             const int f = i & (BC - 1), kc = i >> 5;
-            const float4 a = cr.v[j][0], b = cr.v[j][1];
-            *reinterpret_cast<uint4 *>(cond_img + kc * CHUNK_B + f * 16) = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+            *reinterpret_cast<uint4 *>(cond_img + kc * CHUNK_B + f * 16) = cr.v[j];
         }
     }
 }
@@ -316,7 +382,7 @@ __device__ __forceinline__ void fc_epilogue(uint32_t tmem, int col, uint8_t *sme
     epi_sync();
 }
 
-template <bool PROF>
+template <bool PROF, bool FRAMES>
 __device__ __forceinline__ void dense_body(const DParams &p)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -329,7 +395,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
     if (nf <= 0) return;                                       // whole cluster: nothing to do
     const uint32_t sb = s32(smem);
     const uint32_t bar0 = sb + SM_BAR;
-    int *fold_row0 = reinterpret_cast<int *>(smem + SM_FOLD), *fold_lim = fold_row0 + BC;
+    int *geo = reinterpret_cast<int *>(smem + SM_FOLD);
     Bundle *tab = reinterpret_cast<Bundle *>(smem + SM_TAB);
 
     // ---- set-up: zero the images / conditioning / x, barriers, bundle table, tensor memory
@@ -337,8 +403,12 @@ __device__ __forceinline__ void dense_body(const DParams &p)
     for (int i = tid; i < p.nb * (int)(sizeof(Bundle) / 4); i += DTHREADS) reinterpret_cast<uint32_t *>(tab)[i] = reinterpret_cast<const uint32_t *>(p.table)[i];
     if (tid < BC) {
         const int f = tid;
-        fold_row0[f] = f < nf ? (int)p.fold_start[cfold0 + f] : 0;
-        fold_lim[f] = f < nf ? (int)p.fold_limit[cfold0 + f] : 0;
+        if (FRAMES) {
+            for (int c = 0; c < 4; ++c) geo[c * BC + f] = f < nf ? p.fold_geo[(size_t)(cfold0 + f) * 4 + c] : 0;
+        } else {
+            geo[f] = f < nf ? (int)p.fold_start[cfold0 + f] : 0;
+            geo[BC + f] = f < nf ? (int)p.fold_limit[cfold0 + f] : 0;
+        }
     }
     if (tid == 0) {
         for (int s = 0; s < NSLOT; ++s) {
@@ -499,12 +569,18 @@ __device__ __forceinline__ void dense_body(const DParams &p)
         uint8_t *cond_img = smem + SM_COND;
         CondRegs cr;
         // prologue: conditioning of step 0 -> image, conditioning of step 1 -> registers
-        cond_load(p, fold_row0, fold_lim, nf, tid, 0, cr);
+        CondState cst;
+        if (FRAMES) {
+            cond_state_init(p, geo, tid, cst);
+            cond_load_frames(p, geo, nf, tid, 0, cst, cr);
+        } else
+            cond_load(p, geo, nf, tid, 0, cr);
         cond_store(cond_img, tid, cr);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar0 + B_COND * 8);
-        cond_load(p, fold_row0, fold_lim, nf, tid, 1, cr);
+        if (FRAMES) cond_load_frames(p, geo, nf, tid, 1, cst, cr);
+        else cond_load(p, geo, nf, tid, 1, cr);
 
         unsigned ph = 0;                                        // phase bits of B_ACC + {0..4}, B_X (bit 5), B_LG (bit 6)
         bool ok = true;
@@ -532,7 +608,8 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + B_COND * 8);
-            cond_load(p, fold_row0, fold_lim, nf, tid, t + 2, cr);
+            if (FRAMES) cond_load_frames(p, geo, nf, tid, t + 2, cst, cr);
+            else cond_load(p, geo, nf, tid, t + 2, cr);
             TICK(13);
             // ---- E2: h2(t) = GRU2([x + h1, a2], h2(t-1)) -- :192-194
             ok = mbar_wait(bar0 + (B_ACC + C_G2) * 8, (ph >> C_G2) & 1u, p.status, 21);
@@ -674,7 +751,8 @@ __device__ __forceinline__ void dense_body(const DParams &p)
     if (warp == MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavernn_dense_kernel(const DParams p) { dense_body<false>(p); }
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavernn_dense_kernel_prof(const DParams p) { dense_body<true>(p); }
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavernn_dense_kernel(const DParams p) { dense_body<false, false>(p); }
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavernn_dense_kernel_prof(const DParams p) { dense_body<true, false>(p); }
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(DTHREADS, 1) wavernn_dense_kernel_frames(const DParams p) { dense_body<false, true>(p); }
 
 }   // namespace wrnn_dense

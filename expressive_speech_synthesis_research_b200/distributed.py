@@ -133,16 +133,25 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                 if model.upsample.resnet.conv_in.weight.device != device:
                     model.to(device)
                 wave_len = (mels.size(-1) - 1) * model.hop_length
-                m_up, aux = model.conditioning(mels)
-                L = m_up.size(0)
+                frames = model._frames_mode()                 # dense kernel: conditioning expanded in the kernel, as generate() does
+                if frames:
+                    mel_fr, aux_fr = model.conditioning_frames(mels)
+                    L = mels.size(-1) * model.hop_length
+                else:
+                    m_up, aux = model.conditioning(mels)
+                    L = m_up.size(0)
                 B, _ = _lib.fold_index(L, target, overlap)
                 S = target + 2 * overlap
                 lo, hi = fold_ranges(B, world)[rank]
                 if hi > lo:
                     starts = np.arange(lo, hi, dtype=np.int64) * (target + overlap)
-                    limits = np.full(hi - lo, L, dtype=np.int64)
                     u = None if uniforms is None else torch.as_tensor(uniforms)[:, lo:hi]
-                    res = model._run_folds(eng, device, m_up, aux, starts, limits, S, u, seed + rank, None, False)
+                    if frames:
+                        geo = np.stack([starts, np.full(hi - lo, L), np.zeros(hi - lo), np.zeros(hi - lo)], axis=1)
+                        res = model._run_folds_frames(eng, device, mel_fr, aux_fr, geo, S, u, seed + rank, None, False)
+                    else:
+                        limits = np.full(hi - lo, L, dtype=np.int64)
+                        res = model._run_folds(eng, device, m_up, aux, starts, limits, S, u, seed + rank, None, False)
                     local = res["samples"]
                 else:
                     local = torch.empty(0, S, dtype=torch.float32, device=device)

@@ -178,6 +178,10 @@ class WaveRNN(nn.Module):
         # "fp32" (default, the reference's precision) or "bf16": resident weights rounded to bf16 (after the fp64
         # folding of the input layer), activations and accumulation stay fp32.  Set before calling generate().
         self.precision = "fp32"
+        # precision "bf16-dense" only: expand the conditioning inside the kernel from frame-rate tensors instead
+        # of materialising UpsampleNetwork's [samples, 208] output (832 B per sample).  False = materialise, as the other kernels do.
+        self.expand_in_kernel = True
+        self._interp_cache = None
         self.last_stats = {}
 
     # ------------------------------------------------------------------ engine plumbing
@@ -227,6 +231,87 @@ class WaveRNN(nn.Module):
                 return self.upsample(m)
             finally:
                 torch.backends.cuda.matmul.allow_tf32 = prev
+
+    def _frames_mode(self):
+        return self.precision == "bf16-dense" and self.expand_in_kernel
+
+    def interp_table(self, device=None):
+        """Composite response of UpsampleNetwork's three (Stretch2d, Conv2d box filter) stages (fatchord_version.py:70-77,83-85)
+        as a [hop, 5] fp32 table: for a sample at phase r = (p + pad*hop) % hop of padded frame q = (p + pad*hop) // hop,
+        mel_up[p] = sum_{j<4} table[r, j] * mel_pad[q + table[r, 4] + j].  Measured by pushing an impulse through the layers
+        themselves, so trained filter weights are honoured.  The crop by pad*hop (:85) keeps the zero padding of the intermediate
+        stages out of every retained sample, which is what makes the response phase-periodic."""
+        convs = [self.upsample.up_layers[i] for i in (1, 3, 5)]
+        device = convs[0].weight.device if device is None else device
+        with torch.no_grad():                                               # 2*sum(scales)+3 floats: keyed on their values, not versions
+            tag = (torch.cat([c.weight.detach().flatten() for c in convs]).cpu().numpy().tobytes(), str(device))
+        if self._interp_cache is not None and self._interp_cache[0] == tag:
+            return self._interp_cache[1]
+        hop, n, c = self.hop_length, 9, 4
+        with torch.no_grad():
+            x = torch.zeros(1, 1, 1, n, dtype=torch.float32, device=convs[0].weight.device)
+            x[..., c] = 1.0
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                y = x
+                for layer in self.upsample.up_layers:
+                    y = layer(y)
+            h = y.reshape(n, hop).cpu()                                     # h[k, r]: response at phase r of frame k
+        full = torch.stack([h[c - j] for j in (-2, -1, 0, 1, 2)], dim=1)    # [hop, 5]: weight of frame q + j
+        first = torch.where(full[:, 0] != 0, torch.full((hop,), -2.0), torch.full((hop,), -1.0))
+        table = torch.zeros(hop, 5, dtype=torch.float32)
+        for r in range(hop):
+            s0 = int(first[r].item()) + 2
+            if s0 == 0 and full[r, 4] != 0:
+                raise RuntimeError("interpolation support wider than four frames at phase %d" % r)
+            table[r, :4] = full[r, s0:s0 + 4]
+            table[r, 4] = first[r]
+        if float(h[:c - 2].abs().max()) != 0.0 or float(h[c + 3:].abs().max()) != 0.0:
+            raise RuntimeError("interpolation support wider than the probe")
+        table = table.to(device)
+        self._interp_cache = (tag, table)
+        return table
+
+    def conditioning_frames(self, mels):
+        """Frame-rate view of the prologue (fatchord_version.py:162-165) for the in-kernel expansion:
+        (1, feat, T) -> zero-padded mel frames [T + 2*pad, feat] and MelResNet output [T, 4*aux]."""
+        m = F.pad(mels, (self.pad, self.pad))
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = False
+            try:
+                aux = self.upsample.resnet(m)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        return m[0].t().contiguous(), aux[0].t().contiguous()
+
+    def _run_folds_frames(self, eng, device, mel_frames, aux_frames, geo, S, uniforms, seed, forced_x, return_logits):
+        """wrnn_generate_folds_frames: geo is a host int32 [B, 4] array (sample0, utterance samples, mel frame row, aux frame row)."""
+        geo = np.ascontiguousarray(geo, dtype=np.int32)
+        B = geo.shape[0]
+
+        def dev(t, shape, what):
+            if t is None:
+                return None
+            t = torch.as_tensor(t).to(device=device, dtype=torch.float32).contiguous()
+            if tuple(t.shape) != shape:
+                raise ValueError("%s must have shape %s, got %s" % (what, shape, tuple(t.shape)))
+            return t
+
+        u = dev(uniforms, (S, B), "uniforms")
+        fx = dev(forced_x, (S, B), "forced_x")
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        table = self.interp_table(device)
+        samples = torch.empty(B, S, dtype=torch.float32, device=device)
+        labels = torch.empty(B, S, dtype=torch.int32, device=device)
+        logits = torch.empty(S, B, self.n_classes, dtype=torch.float32, device=device) if return_logits else None
+        stream = torch.cuda.current_stream(device).cuda_stream
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        _lib.check(eng.lib.wrnn_generate_folds_frames(
+            eng.handle, ptr(mel_frames), mel_frames.size(0), ptr(aux_frames), aux_frames.size(0), ptr(table),
+            self.hop_length, self.pad, geo.ctypes.data_as(ctypes.c_void_p), B, S,
+            ptr(u), ctypes.c_uint64(seed), ptr(fx), ptr(logits), ptr(samples), ptr(labels), ctypes.c_void_p(stream)))
+        return dict(samples=samples, labels=labels, logits=logits)
 
     # ------------------------------------------------------------------ the hot path
     def generate(self, mels, *args, uniforms=None, seed=None, forced_x=None, return_logits=False,
@@ -293,8 +378,13 @@ class WaveRNN(nn.Module):
         if wave_len < tail:
             raise ValueError("operands could not be broadcast together: wave_len %d < 20*hop_length %d "
                              "(the reference needs T >= 21 frames, fatchord_version.py:235-237)" % (wave_len, tail))
-        m_up, aux = self.conditioning(mels)                           # :164-165
-        L = m_up.size(0)
+        frames = self._frames_mode()
+        if frames:
+            mel_fr, aux_fr = self.conditioning_frames(mels)           # :164 at frame rate; :165 happens inside the kernel
+            L = T * self.hop_length
+        else:
+            m_up, aux = self.conditioning(mels)                       # :164-165
+            L = m_up.size(0)
         if batched:
             B, _ = _lib.fold_index(L, target, overlap)                # :298-309
             if B <= 0:
@@ -304,8 +394,12 @@ class WaveRNN(nn.Module):
         else:
             B, S = 1, L
             starts = np.zeros(1, dtype=np.int64)
-        limits = np.full(B, L, dtype=np.int64)
-        res = self._run_folds(eng, device, m_up, aux, starts, limits, S, uniforms, seed, forced_x, return_logits)
+        if frames:
+            geo = np.stack([starts, np.full(B, L), np.zeros(B), np.zeros(B)], axis=1)
+            res = self._run_folds_frames(eng, device, mel_fr, aux_fr, geo, S, uniforms, seed, forced_x, return_logits)
+        else:
+            limits = np.full(B, L, dtype=np.int64)
+            res = self._run_folds(eng, device, m_up, aux, starts, limits, S, uniforms, seed, forced_x, return_logits)
         wav = torch.empty(wave_len, dtype=torch.float64, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
         _lib.check(eng.lib.wrnn_xfade_unfold(res["samples"].data_ptr(), B, S, int(batched), overlap if batched else 0,
@@ -394,26 +488,43 @@ class WaveRNN(nn.Module):
                         chunks.append(cur)
                     stream = torch.cuda.current_stream(device).cuda_stream
                     outs, fold0, kernel_ms = [None] * len(plan), 0, 0.0
+                    frames = self._frames_mode()
                     for ci, chunk in enumerate(chunks):
-                        rows = sum(plan[i][1] for i in chunk)
-                        m_all = torch.empty(rows, self._feat_dims, dtype=torch.float32, device=device)
-                        a_all = torch.empty(rows, 4 * self.aux_dims, dtype=torch.float32, device=device)
-                        starts, limits, base = [], [], 0
-                        for i in chunk:
-                            B, L, _ = plan[i]
-                            m_up, aux = self.conditioning(mel_list[i].to(device=device, dtype=torch.float32))
-                            if m_up.size(0) != L:
-                                raise RuntimeError("conditioning network returned %d rows, expected %d" % (m_up.size(0), L))
-                            m_all[base:base + L].copy_(m_up)
-                            a_all[base:base + L].copy_(aux)
-                            del m_up, aux
-                            starts.append(base + np.arange(B, dtype=np.int64) * (target + overlap))
-                            limits.append(np.full(B, base + L, dtype=np.int64))
-                            base += L
                         nf = sum(plan[i][0] for i in chunk)
                         u = None if uniforms is None else uniforms[:, fold0:fold0 + nf].contiguous()
                         sd = None if seed is None else int(seed) + ci        # in-kernel draws: one Philox stream per chunk
-                        res = self._run_folds(eng, device, m_all, a_all, np.concatenate(starts), np.concatenate(limits), S, u, sd, None, False)
+                        if frames:
+                            mfs, afs, geo, mb, ab = [], [], [], 0, 0
+                            for i in chunk:
+                                B, L, _ = plan[i]
+                                mf, af = self.conditioning_frames(mel_list[i].to(device=device, dtype=torch.float32))
+                                mfs.append(mf)
+                                afs.append(af)
+                                g = np.zeros((B, 4), dtype=np.int64)
+                                g[:, 0] = np.arange(B, dtype=np.int64) * (target + overlap)
+                                g[:, 1], g[:, 2], g[:, 3] = L, mb, ab
+                                geo.append(g)
+                                mb += mf.size(0)
+                                ab += af.size(0)
+                            m_all, a_all = torch.cat(mfs), torch.cat(afs)
+                            res = self._run_folds_frames(eng, device, m_all, a_all, np.concatenate(geo), S, u, sd, None, False)
+                        else:
+                            rows = sum(plan[i][1] for i in chunk)
+                            m_all = torch.empty(rows, self._feat_dims, dtype=torch.float32, device=device)
+                            a_all = torch.empty(rows, 4 * self.aux_dims, dtype=torch.float32, device=device)
+                            starts, limits, base = [], [], 0
+                            for i in chunk:
+                                B, L, _ = plan[i]
+                                m_up, aux = self.conditioning(mel_list[i].to(device=device, dtype=torch.float32))
+                                if m_up.size(0) != L:
+                                    raise RuntimeError("conditioning network returned %d rows, expected %d" % (m_up.size(0), L))
+                                m_all[base:base + L].copy_(m_up)
+                                a_all[base:base + L].copy_(aux)
+                                del m_up, aux
+                                starts.append(base + np.arange(B, dtype=np.int64) * (target + overlap))
+                                limits.append(np.full(B, base + L, dtype=np.int64))
+                                base += L
+                            res = self._run_folds(eng, device, m_all, a_all, np.concatenate(starts), np.concatenate(limits), S, u, sd, None, False)
                         kernel_ms += eng.info().last_kernel_ms
                         b0 = 0
                         for i in chunk:

@@ -129,6 +129,29 @@ int32_t wrnn_generate_folds(wrnn_handle *h,
                             float *samples_out, int32_t *labels_out, void *stream);
 
 /*
+ * The same step loop with the conditioning EXPANDED IN THE KERNEL from frame-rate tensors: the three
+ * (Stretch2d, box-filter Conv2d) stages of UpsampleNetwork.forward, the repeat of the MelResNet output (fatchord_version.py:
+ * 79-86) and fold_with_overlap's gather (:311-319) are fused into the kernel's conditioning load, so the [samples, 208] fp32
+ * tensors (832 B per sample) are never materialised.  WRNN_PREC_BF16_DENSE handles only; others fail with WRNN_ERR_INVALID.
+ *
+ *   mel_frames [dev] float32 [frame_rows, feat_dims]   mel frames of every utterance, zero-padded by `pad` frames on both sides
+ *   aux_frames [dev] float32 [aux_rows, 4*aux_dims]    MelResNet output (one row per unpadded frame)
+ *   interp     [dev] float32 [hop, 5]   per phase r = (sample + pad*hop) % hop: four weights of the composite response of the
+ *                                       (repeat, FIR) stages and the offset (-2 or -1, stored as float) of the first frame they apply to
+ *   fold_geo   [host] int32 [num_folds, 4]  first sample of the fold within its utterance, samples of the utterance (rows beyond
+ *                                       are the zero padding of :306-309), row of the utterance's first padded mel frame, row of its
+ *                                       first aux frame
+ * Remaining arguments as in wrnn_generate_folds.
+ */
+int32_t wrnn_generate_folds_frames(wrnn_handle *h,
+                                   const float *mel_frames, int64_t frame_rows, const float *aux_frames, int64_t aux_rows,
+                                   const float *interp, int32_t hop, int32_t pad,
+                                   const int32_t *fold_geo, int32_t num_folds, int32_t steps,
+                                   const float *uniforms, uint64_t seed,
+                                   const float *forced_x, float *logits_out,
+                                   float *samples_out, int32_t *labels_out, void *stream);
+
+/*
  * generate() epilogue on the device, fatchord_version.py:222-237:
  * widen to float64, xfade_and_unfold (:321-383, bit-exact: mul and add kept separate),
  * optional decode_mu_law (utility/dsp.py:100-105; pow within 2 ulp), trim to wave_len,

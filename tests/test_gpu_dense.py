@@ -143,3 +143,31 @@ def test_dense_generate_many_chunks_match_single_utterance_calls():
             single = m.generate(mm, True, t, o, True, uniforms=U[:, b0:b0 + nb])
             assert np.array_equal(single, wav), k
         b0 += nb
+
+
+def test_dense_in_kernel_conditioning_expansion_matches_the_materialised_path():
+    """generate() on the dense kernel expands the conditioning inside the kernel from frame-rate tensors.  On the
+    same utterance and draws the teacher-forced logits must agree with the path that materialises UpsampleNetwork's output
+    (both round the conditioning to bf16: a last-bit difference of the fp32 value can move one bf16 ulp) and with the fp64 oracle."""
+    m = dense_model()
+    sd = synth.make_state("RAW", "ref", 0)
+    T, target, overlap = 64, 900, 60
+    mel = synth.make_mel(T, seed=9)
+    S = target + 2 * overlap
+    B = c_oracle.fold_index(T * 200, target, overlap)[0]
+    U = synth.make_uniforms(S, B, "RAW", seed=10)
+    forced = np.random.default_rng(13).uniform(-1, 1, (S, B)).astype(np.float32)
+    out = {}
+    for mode in (True, False):
+        m.expand_in_kernel = mode
+        try:
+            _, ex = m.generate(mel, True, target, overlap, True, uniforms=U, forced_x=forced, return_logits=True)
+        finally:
+            m.expand_in_kernel = True
+        out[mode] = ex["logits"].cpu().numpy()
+    assert np.abs(out[True] - out[False]).max() <= 1e-3
+    mf, af = H.folded_conditioning(sd, mel, "ref", True, target, overlap)
+    want = c_oracle.generate_folds(sd, "RAW", mf, af, U.numpy(), forced_x=forced, want_logits=True, precision="fp64")["logits"]
+    assert np.abs(out[True] - want).max() <= TOL_DENSE_LOGITS
+    # unbatched: one fold over the whole utterance
+    m.generate(synth.make_mel(22, seed=11), False, target, overlap, True, seed=1)
