@@ -380,9 +380,9 @@ static void finish_images(int rows5, int bf16w, const std::vector<float> &img32,
 // ---- precision bf16-dense: operand stream, bundle table and per-row vectors of csrc/wavernn_dense.cuh ------------
 // One step of the tensor-core program, in issue order (wavernn_dense.cuh has the dependency argument):
 //   (a) after h1(t):  Wih2x.h1 -> g2 [commit G2] | Wfc1x.h1 -> f1 | P1.c(t+1) -> g1 (first touch)
-//   (b) after h2(t):  Wfc1x.h2 -> f1 [commit F1] | P2.c(t+1) -> g2 (first touch)
-//   (c) after y1(t):  Wfc2x.y1 -> f2 [commit F2] | P3.c(t+1) -> f1 (first touch)
-//   (d) after y2(t):  Wfc3.y2 -> f3 (first touch) [commit F3] | P4 -> f2 (first touch) | Whh1.h1 -> g1 [commit G1] | Whh2.h2 -> g2 [commit H2RD]
+//   (b) after h2(t):  Wfc1x.h2 -> f1 [commit F1] | P2.c(t+1) -> g2 (first touch) | Whh2.h2 -> g2 (1 of 6 bundles)
+//   (c) after y1(t):  Wfc2x.y1 -> f2 [commit F2] | P3.c(t+1) -> f1 (first touch) | Whh2.h2 (2 of 6)
+//   (d) after y2(t):  Wfc3.y2 -> f3 (first touch) [commit F3] | P4 -> f2 (first touch) | Whh1.h1 -> g1 [commit G1] | Whh2.h2 (3 of 6) [commit H2RD]
 // The part after each "|" is work for step t+1 placed where the tensor pipe would otherwise wait for an epilogue + exchange.
 // Tiles: T0 = [r | z] rows of the CTA's 64 units (128 rows), T1 = the n rows (64), F = 64 fc rows / classes.
 namespace {
@@ -450,6 +450,21 @@ static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
             prog.push_back(b);
         }
     };
+    // single bundles of a K = 512 product, for work that is spread over several gaps
+    auto t0_block = [&](int commit, int bimg, const float *W, int ld, int dT0, int kb, int first) {
+        DenseBundle b;
+        b.wait = W_NONE;
+        b.commit = commit;
+        b.segs.push_back(DenseSeg(128, 8, img(bimg, kb * 16), dT0, first, [=](int rank, int m, int k) { return (double)W[(size_t)rowT0(rank, m) * ld + kb * 128 + k]; }));
+        prog.push_back(b);
+    };
+    auto t1_half = [&](int commit, int bimg, const float *W, int ld, int dT1, int half, int first) {
+        DenseBundle b;
+        b.wait = W_NONE;
+        b.commit = commit;
+        b.segs.push_back(DenseSeg(UPC, 16, img(bimg, half * 32), dT1, first, [=](int rank, int m, int k) { return (double)W[(size_t)rowN(rank, m) * ld + half * 256 + k]; }));
+        prog.push_back(b);
+    };
     auto fc = [&](int wait, int commit, int bimg, const float *W, int ld, int dcol, int first, bool classes) {
         for (int half = 0; half < 2; ++half) {
             DenseBundle b;
@@ -480,16 +495,22 @@ static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
     one(W_NONE, C_NONE, {DenseSeg(128, 8, cnd(0), D_G2_T0, 1, [=](int rank, int m, int k) { return p2(rowT0(rank, m), k); })});
     one(W_NONE, C_NONE, {DenseSeg(128, 1, cnd(16), D_G2_T0, 0, [=](int rank, int m, int k) { return p2(rowT0(rank, m), 128 + k); }),
                          DenseSeg(UPC, 9, cnd(0), D_G2_1I, 1, [=](int rank, int m, int k) { return p2(rowN(rank, m), k); })});
-    // (c) critical: Wfc2x.y1 -> f2.  Inside E4 + the y2 exchange: P3.c(t+1) -> f1 (first touch; E3(t) has drained f1)
+    // Whh2.h2(t) (step t+1's hidden-side gates) is spread over the gaps of (b), (c) and the tail of (d): the n rows' first half here
+    t1_half(C_NONE, IMG_H2, w->r2_whh, R, D_G2_1H, 0, 1);
+    // (c) critical: Wfc2x.y1 -> f2.  Inside E4 + the y2 exchange: P3.c(t+1) -> f1 (first touch; E3(t) has drained f1), Whh2 [r | z] K 0..255
     fc(W_Y1, C_F2, IMG_Y1, w->fc2_w, RA, D_F2, 0, false);
     one(W_NONE, C_NONE, {DenseSeg(UPC, 7, cnd(0), D_F1, 1, [=](int rank, int m, int k) { return g3[(size_t)unit(rank, m) * KC + k]; }),
                          DenseSeg(UPC, 2, cnd(18), D_F1, 0, [=](int rank, int m, int k) { return (double)f1[(size_t)unit(rank, m) * RA + R + k]; })});
+    t0_block(C_NONE, IMG_H2, w->r2_whh, R, D_G2_T0, 0, 0);
+    t0_block(C_NONE, IMG_H2, w->r2_whh, R, D_G2_T0, 1, 0);
     // (d) critical: Wfc3.y2 -> f3.  Inside E5, the logits exchange, sampling and E1(t+1): P4 -> f2 (first touch), Whh1.h1(t) -> g1
     // [commit G1: E1(t+1) may start], then Whh2.h2(t) -> g2 [commit H2RD: this CTA no longer reads the h2(t) image]
     fc(W_Y2, C_F3, IMG_Y2, w->fc3_w, R, D_F3, 1, true);
     one(W_NONE, C_NONE, {DenseSeg(UPC, 2, cnd(22), D_F2, 1, [=](int rank, int m, int k) { return (double)f2[(size_t)unit(rank, m) * RA + R + k]; })});
     hidden(W_NONE, C_G1, IMG_H1, w->r1_whh, R, D_G1_T0, D_G1_1H, 0, 1);
-    hidden(W_NONE, C_H2RD, IMG_H2, w->r2_whh, R, D_G2_T0, D_G2_1H, 0, 1);
+    t0_block(C_NONE, IMG_H2, w->r2_whh, R, D_G2_T0, 2, 0);
+    t0_block(C_NONE, IMG_H2, w->r2_whh, R, D_G2_T0, 3, 0);
+    t1_half(C_H2RD, IMG_H2, w->r2_whh, R, D_G2_1H, 1, 0);
     if ((int)prog.size() > MAXBUNDLE) return fail(WRNN_ERR_INVALID, "dense program has %zu bundles (max %d)", prog.size(), MAXBUNDLE);
 
     // serialise: table (identical for every rank) and the per-rank streams

@@ -116,29 +116,38 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, unsigned count) { asm vo
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) { asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory"); }
+// CTA-scope acquire is enough for everything that completes through the async proxy (TMA fill, DSMEM bulk copies, tcgen05.commit)
+// or through local arrivals.  Only the sample broadcast (a remote generic store followed by a remote arrive) needs cluster scope,
+// and ptxas follows every cluster-scope acquire with CCTL.IVALL, which throws the L1 contents away.
+template <bool CLUSTER>
 __device__ __forceinline__ bool mbar_try(uint32_t bar, unsigned parity)
 {
     unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (CLUSTER)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
 // capped wait (~1 s): a stuck pipeline sets *status and lets every role run out instead of hanging the GPU
+template <bool CLUSTER>
 __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, unsigned parity, int *status, int code)
 {
     const long long t0 = clock64();
     for (;;) {
         for (int i = 0; i < 256; ++i)
-            if (mbar_try(bar, parity)) return true;
+            if (mbar_try<CLUSTER>(bar, parity)) return true;
         if (clock64() - t0 > 2000000000ll) {
             atomicCAS(status, 0, code);
             return false;
         }
     }
 }
+template <bool CLUSTER = false>
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, unsigned parity, int *status, int code)
 {
-    if (mbar_try(bar, parity)) return true;
-    return mbar_wait_slow(bar, parity, status, code);
+    if (mbar_try<CLUSTER>(bar, parity)) return true;
+    return mbar_wait_slow<CLUSTER>(bar, parity, status, code);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, unsigned bytes, uint32_t bar)
 {
@@ -594,7 +603,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             if (!ok) break;
             TICK(0);
             if (t > 0) {
-                ok = mbar_wait(bar0 + B_X * 8, (ph >> 5) & 1u, p.status, 25);
+                ok = mbar_wait<true>(bar0 + B_X * 8, (ph >> 5) & 1u, p.status, 25);
                 ph ^= 1u << 5;
                 if (!ok) break;
             }
@@ -608,8 +617,6 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + B_COND * 8);
-            if (FRAMES) cond_load_frames(p, geo, nf, tid, t + 2, cst, cr);
-            else cond_load(p, geo, nf, tid, t + 2, cr);
             TICK(13);
             // ---- E2: h2(t) = GRU2([x + h1, a2], h2(t-1)) -- :192-194
             ok = mbar_wait(bar0 + (B_ACC + C_G2) * 8, (ph >> C_G2) & 1u, p.status, 21);
@@ -632,6 +639,10 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             fc_epilogue(tmem, D_F1, smem, IMG_Y1, rank, warp, lane, b3, u3);
             if (warp == 0) send_slice(sb, IMG_Y1, rank, lane);
             TICK(9);
+            // conditioning of step t+2 -> registers (bf16): the global-load latency it waits for hides in the wait for fc2's products
+            if (FRAMES) cond_load_frames(p, geo, nf, tid, t + 2, cst, cr);
+            else cond_load(p, geo, nf, tid, t + 2, cr);
+            TICK(13);
             // ---- E4: y2 = relu(fc2([y1, a4])) -- :200-201
             ok = mbar_wait(bar0 + (B_ACC + C_F2) * 8, (ph >> C_F2) & 1u, p.status, 23);
             ph ^= 1u << C_F2;

@@ -23,6 +23,13 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint32_t a_lo, uint32_t 
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate));
 }
 struct Seg { uint16_t off16, rows, nk, bsrc16, dcol, first; };
+template <int NK>
+__device__ __forceinline__ void issue_run(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t a_inc, uint32_t hi, uint32_t idesc, uint32_t acc0)
+{
+    tc_mma(d, a_lo, b_lo, hi, idesc, acc0);
+#pragma unroll
+    for (int k = 1; k < NK; ++k) tc_mma(d, a_lo + k * a_inc, b_lo + k * 64, hi, idesc, 1u);
+}
 // flags: 1 = wait on the (self-completing) ring barrier per bundle, 2 = tcgen05.fence::after_thread_sync per bundle, 4 = commit to an "empty" barrier
 // per bundle (which a producer-like thread turns into the next "full"), 8 = segment record read from shared memory (else registers)
 __global__ void __launch_bounds__(384, 1) issue_kernel(int flags, int nk, int nbundles, long long *out)
@@ -67,18 +74,24 @@ __global__ void __launch_bounds__(384, 1) issue_kernel(int flags, int nk, int nb
                     if (flags & 2) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t slot_base = sb + slot * 32768;
                     Seg sg;
-                    if (flags & 8) sg = segs[0]; else sg = Seg{0, 128, (uint16_t)nk, 0, 0, 1};
+                    if (flags & 8) sg = segs[0]; else sg = Seg{0, 128, (uint16_t)nk, 0, (uint16_t)((flags & 128) ? 64 * (b & 1) : 0), (uint16_t)((flags & 64) ? 0 : 1)};
                     const uint32_t rows = sg.rows, d = tmem + sg.dcol;
                     uint32_t a_lo = (((slot_base + sg.off16 * 16u) & 0x3FFFFu) >> 4) | ((rows * 16u >> 4) << 16);
                     uint32_t b_lo = (((sb + 65536u + sg.bsrc16 * 16u) & 0x3FFFFu) >> 4) | ((512u >> 4) << 16);
                     const uint32_t a_inc = rows * 2;
-                    tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, sg.first ? 0u : 1u);
                     const int n = sg.nk;
+                    if (flags & 32) {
+                        if (n == 8) issue_run<8>(d, a_lo, b_lo, a_inc, DESC_HI, IDESC, sg.first ? 0u : 1u);
+                        else if (n == 16) issue_run<16>(d, a_lo, b_lo, a_inc, DESC_HI, IDESC, sg.first ? 0u : 1u);
+                        else issue_run<1>(d, a_lo, b_lo, a_inc, DESC_HI, IDESC, sg.first ? 0u : 1u);
+                    } else {
+                        tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, sg.first ? 0u : 1u);
 #pragma unroll 4
-                    for (int k = 1; k < n; ++k) {
-                        a_lo += a_inc;
-                        b_lo += 64;
-                        tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, 1u);
+                        for (int k = 1; k < n; ++k) {
+                            a_lo += a_inc;
+                            b_lo += 64;
+                            tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, 1u);
+                        }
                     }
                     if (flags & 4) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(&empty[slot])) : "memory");
                 }
@@ -93,7 +106,7 @@ __global__ void __launch_bounds__(384, 1) issue_kernel(int flags, int nk, int nb
             const uint32_t slot_base = sb + slot * 32768;
             if (elect_one()) {
                 Seg sg;
-                if (flags & 8) sg = segs[0]; else sg = Seg{0, 128, (uint16_t)nk, 0, 0, 1};
+                if (flags & 8) sg = segs[0]; else sg = Seg{0, 128, (uint16_t)nk, 0, (uint16_t)((flags & 128) ? 64 * (b & 1) : 0), (uint16_t)((flags & 64) ? 0 : 1)};
                 const uint32_t rows = sg.rows, d = tmem + sg.dcol;
                 uint32_t a_lo = (((slot_base + sg.off16 * 16u) & 0x3FFFFu) >> 4) | ((rows * 16u >> 4) << 16);
                 uint32_t b_lo = (((sb + 65536u + sg.bsrc16 * 16u) & 0x3FFFFu) >> 4) | ((512u >> 4) << 16);
@@ -127,10 +140,10 @@ int main()
     CK(cudaMalloc(&d, 16));
     CK(cudaFuncSetAttribute(issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     const int nb = 500;
-    const int fl[] = {0, 8, 2, 1, 3, 4, 6, 14, 16, 30};
+    const int fl[] = {0, 8, 2, 1, 3, 4, 6, 14, 16, 30, 48, 62, 16 + 64, 16 + 128, 16 + 64 + 128};
     const char *nm[] = {"bare", "segment record from shared memory", "+ tcgen05.fence per bundle", "+ wait on a completed mbarrier per bundle", "+ wait + fence",
-                        "ring: commit -> empty -> full -> wait", "ring + fence", "ring + fence + record from shared memory (the kernel)", "bare, ONE elect region around the whole loop", "the kernel, ONE elect region around the whole loop"};
-    for (int v = 0; v < 10; ++v)
+                        "ring: commit -> empty -> full -> wait", "ring + fence", "ring + fence + record from shared memory (the kernel)", "bare, ONE elect region around the whole loop", "the kernel, ONE elect region around the whole loop", "bare, ONE region, constant-count straight-line issue", "the kernel, ONE region, straight-line issue", "bare ONE region, every bundle ACCUMULATES into the same D", "bare ONE region, overwrite, alternating between two D", "bare ONE region, accumulate, alternating between two D"};
+    for (int v = 0; v < 15; ++v)
         for (int nk : {8, 16}) {
             issue_kernel<<<1, 384, 200 * 1024>>>(fl[v], nk, nb, d);
             CK(cudaDeviceSynchronize());
