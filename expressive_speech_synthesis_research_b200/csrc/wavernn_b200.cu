@@ -94,8 +94,8 @@ static int32_t derive_layout(const wrnn_config &c, int &rows5, int &nprod5, int 
         return fail(WRNN_ERR_INVALID, "conditioning layout is fixed to feat_dims 80 + 4 x aux_dims 32 (got %d, %d)", c.feat_dims, c.aux_dims);
     if (c.precision != WRNN_PREC_FP32 && c.precision != WRNN_PREC_BF16 && c.precision != WRNN_PREC_BF16_DENSE)
         return fail(WRNN_ERR_INVALID, "unknown precision %d", c.precision);
-    if (c.precision == WRNN_PREC_BF16_DENSE && !(c.mode == WRNN_MODE_RAW && c.n_classes == wrnn_dense::NCLASS))
-        return fail(WRNN_ERR_INVALID, "precision bf16-dense (tcgen05 path) is built for RAW mode with %d classes", wrnn_dense::NCLASS);
+    if (c.precision == WRNN_PREC_BF16_DENSE && !((c.mode == WRNN_MODE_RAW && c.n_classes == wrnn_dense::NCLASS) || (c.mode == WRNN_MODE_MOL && c.n_classes == wrnn_dense::MOL_C)))
+        return fail(WRNN_ERR_INVALID, "precision bf16-dense (tcgen05 path) is built for RAW with %d classes and MOL with %d outputs", wrnn_dense::NCLASS, wrnn_dense::MOL_C);
     if (c.mode == WRNN_MODE_RAW) {
         const int C = c.n_classes;
         if (C != 64 && C != 128 && C != 256 && C != 512 && C != 1024)
@@ -403,7 +403,7 @@ struct DensePack {
     unsigned stream_bytes = 0;
 };
 
-static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
+static int32_t pack_dense(int C, const wrnn_weights *w, DensePack &out)
 {
     using namespace wrnn_dense;
     const int R = DHID, F = 80, A = 32, KI = 1 + F + A, KC = F + A, RA = R + A;
@@ -470,7 +470,9 @@ static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
             DenseBundle b;
             b.wait = half == 0 ? wait : W_NONE;
             b.commit = half == 1 ? commit : C_NONE;
-            b.segs.push_back(DenseSeg(UPC, 16, img(bimg, half * 32), dcol, first && half == 0, [=](int rank, int m, int k) { (void)classes; return (double)W[(size_t)unit(rank, m) * ld + half * 256 + k]; }));
+            // fc3: output row 64 rank + m exists only below C (MOL: the 30 outputs are rows 0-29 of rank 0, everything else is zero)
+            b.segs.push_back(DenseSeg(UPC, 16, img(bimg, half * 32), dcol, first && half == 0, [=](int rank, int m, int k) {
+                return classes && unit(rank, m) >= C ? 0.0 : (double)W[(size_t)unit(rank, m) * ld + half * 256 + k]; }));
             prog.push_back(b);
         }
     };
@@ -566,7 +568,7 @@ static int32_t pack_dense(const wrnn_weights *w, DensePack &out)
             sv[DV_B3 * UPC + m] = (float)(c3[ur] + (double)w->fc1_b[ur]);
             sv[DV_U3 * UPC + m] = (float)u3[ur];
             sv[DV_B4 * UPC + m] = w->fc2_b[ur];
-            sv[DV_B5 * UPC + m] = w->fc3_b[ur];
+            sv[DV_B5 * UPC + m] = ur < C ? w->fc3_b[ur] : 0.f;
         }
     }
     return WRNN_OK;
@@ -585,7 +587,7 @@ extern "C" int32_t wrnn_dense_layout(const wrnn_config *cfg, int64_t *layout)
     std::vector<float> z((size_t)1536 * 544, 0.f);
     wrnn_weights w = {z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data(), z.data()};
     DensePack dp;
-    rc = pack_dense(&w, dp);
+    rc = pack_dense(c.n_classes, &w, dp);
     if (rc) return rc;
     const int64_t v[8] = {(int64_t)dp.table.size(), dp.stream_bytes, (int64_t)sizeof(Bundle), wrnn_dense::CL, wrnn_dense::UPC, wrnn_dense::BC, wrnn_dense::NSV, 0};
     memcpy(layout, v, sizeof v);
@@ -601,7 +603,7 @@ extern "C" int32_t wrnn_dense_pack_host(const wrnn_config *cfg, const wrnn_weigh
     int32_t rc = derive_layout(c, rows5, nprod5, n_u);
     if (rc) return rc;
     DensePack dp;
-    rc = pack_dense(w, dp);
+    rc = pack_dense(c.n_classes, w, dp);
     if (rc) return rc;
     memcpy(stream, dp.stream.data(), dp.stream.size());
     memcpy(table, dp.table.data(), dp.table.size() * sizeof(Bundle));
@@ -641,7 +643,7 @@ extern "C" int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w)
     CUDA_TRY(cudaSetDevice(h->device));
     if (h->dense) {
         DensePack dp;
-        int32_t rc = pack_dense(w, dp);
+        int32_t rc = pack_dense(h->cfg.n_classes, w, dp);
         if (rc) return rc;
         cudaFree(h->dense_stream);
         cudaFree(h->dense_table);
@@ -759,6 +761,7 @@ static int32_t launch_dense(wrnn_handle *h, wrnn_dense::DParams dp, bool frames,
         dp.nfolds = nb;
         dp.per = (nb + ncl - 1) / ncl;
         dp.prof = nullptr;
+        dp.mol = h->cfg.mode == WRNN_MODE_MOL ? 1 : 0;
         if (h->profiling && !frames) {
             if (!h->dense_prof) CUDA_TRY(cudaMalloc(&h->dense_prof, (size_t)h->dense_clusters * CL * PROF_N * sizeof(long long)));
             CUDA_TRY(cudaMemsetAsync(h->dense_prof, 0, (size_t)h->dense_clusters * CL * PROF_N * sizeof(long long), st));

@@ -40,6 +40,7 @@ constexpr int COND_CHUNKS = 26;               // 208 conditioning inputs: mel 80
 constexpr int COND_B = COND_CHUNKS * CHUNK_B;
 constexpr int SLICE_B = (UPC / 8) * CHUNK_B;  // a CTA's 64 units of an image
 constexpr int NCLASS = 512;                   // RAW 9 bit
+constexpr int MOL_C = 30, MOL_NR = 10, MOL_NU = 11;   // MOL: 10 mixtures x (logit, mean, log scale); 10 + 1 uniforms per draw
 constexpr int FPC = BC / CL;                  // folds sampled by each CTA
 constexpr int MAXSEG = 4, MAXBUNDLE = 40;
 constexpr int NSV = 18;                       // per-row fp32 vectors (biases, x coefficients), [NSV][UPC] per CTA
@@ -92,6 +93,7 @@ struct DParams {
     const int *fold_geo;           // [B][4]: first sample of the fold in its utterance, samples of the utterance, row of the
                                    // utterance's first (padded) mel frame, row of its first aux frame
     int hop, indent;               // samples per frame, pad * hop
+    int mol;                       // 0: RAW, 512 classes (softmax + inverse CDF); 1: MOL, 30 outputs (discretized mix of logistics)
     const float *uniforms, *forced_x;
     float *logits_out, *samples_out;
     int *labels_out;
@@ -208,9 +210,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi)
 }
 
 // Philox4x32-10, same stream as the fp32 kernel: uniform j of (step, fold) = word j & 3 of Philox({step, fold, j >> 2, 0}, seed)
-__device__ __forceinline__ float philox_u01(unsigned long long seed, int step, int fold)
+__device__ __forceinline__ float philox_u01(unsigned long long seed, int step, int fold, int j = 0)
 {
-    uint4 c = make_uint4((unsigned)step, (unsigned)fold, 0u, 0u);
+    uint4 c = make_uint4((unsigned)step, (unsigned)fold, (unsigned)(j >> 2), 0u);
     uint2 k = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
 #pragma unroll 1
     for (int i = 0; i < 10; ++i) {
@@ -220,7 +222,8 @@ __device__ __forceinline__ float philox_u01(unsigned long long seed, int step, i
         k.x += 0x9E3779B9u;
         k.y += 0xBB67AE85u;
     }
-    return (float)(c.x >> 8) * (1.0f / 16777216.0f);
+    const unsigned w = (j & 3) == 0 ? c.x : (j & 3) == 1 ? c.y : (j & 3) == 2 ? c.z : c.w;
+    return (float)(w >> 8) * (1.0f / 16777216.0f);
 }
 
 // ---- conditioning: item (kc, f) = 8 consecutive conditioning inputs of fold f, fp32 in global, bf16 in the image ----
@@ -685,15 +688,61 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             if (warp < FPC) {
                 const int fl = FPC * (int)rank + warp;          // fold within the cluster
                 const int bglob = cfold0 + fl;
-                float uu = 0.f, fx = 0.f;                       // the draw and the forced value are fetched while the logits travel
-                if (lane == 0 && fl < nf) {
-                    uu = p.uniforms ? __ldg(p.uniforms + (size_t)t * p.B + bglob) : philox_u01(p.seed, t, bglob);
-                    if (p.forced_x) fx = __ldg(p.forced_x + (size_t)t * p.B + bglob);
+                float uu = 0.f, fx = 0.f;                       // the draws and the forced value are fetched while the logits travel
+                if (fl < nf) {
+                    if (p.mol) {                                // lane j < 11: uniform j of this (step, fold)
+                        if (lane < MOL_NU) uu = p.uniforms ? __ldg(p.uniforms + ((size_t)t * p.B + bglob) * MOL_NU + lane) : philox_u01(p.seed, t, bglob, lane);
+                    } else if (lane == 0)
+                        uu = p.uniforms ? __ldg(p.uniforms + (size_t)t * p.B + bglob) : philox_u01(p.seed, t, bglob);
+                    if (lane == 0 && p.forced_x) fx = __ldg(p.forced_x + (size_t)t * p.B + bglob);
                 }
                 ok = mbar_wait(bar0 + B_LG * 8, (ph >> 6) & 1u, p.status, 26);
                 ph ^= 1u << 6;
                 if (!ok) break;
                 TICK(6);
+                if (p.mol) {
+                    // sample_from_discretized_mix_logistic (utility/distribution.py:87-123) as in the fp32 kernel: the 30 outputs are
+                    // rows 0-29 of CTA 0's tile; lane i < 10 scores mixture i (Gumbel-max), lane 0 draws from the chosen logistic
+                    const float *l30 = reinterpret_cast<const float *>(smem + SM_SAMP) + warp * UPC;     // source CTA 0, fold `warp`
+                    if (p.logits_out && fl < nf && lane < MOL_C) p.logits_out[((size_t)t * p.B + bglob) * MOL_C + lane] = l30[lane];
+                    float best = -INFINITY;
+                    int arg = 1 << 20;
+                    if (lane < MOL_NR) {
+                        const float u = (float)(1e-5 + ((1.0 - 1e-5) - 1e-5) * (double)uu);
+                        best = l30[lane] - logf(-logf(u));
+                        arg = lane;
+                    }
+#pragma unroll
+                    for (int off = 1; off <= 8; off <<= 1) {
+                        const float b2 = __shfl_xor_sync(0xffffffffu, best, off);
+                        const int a2 = __shfl_xor_sync(0xffffffffu, arg, off);
+                        if (b2 > best || (b2 == best && a2 < arg)) {
+                            best = b2;
+                            arg = a2;
+                        }
+                    }
+                    arg = __shfl_sync(0xffffffffu, arg, 0);
+                    const float u2r = __shfl_sync(0xffffffffu, uu, MOL_NR);
+                    float x = 0.f;
+                    if (lane == 0 && fl < nf) {
+                        const float mean = l30[MOL_NR + arg];
+                        const float ls = fmaxf(l30[2 * MOL_NR + arg], -32.23619130191664f);
+                        const float u2 = (float)(1e-5 + ((1.0 - 1e-5) - 1e-5) * (double)u2r);
+                        x = mean + expf(ls) * (logf(u2) - logf(1.0f - u2));
+                        x = fminf(fmaxf(x, -1.0f), 1.0f);
+                        p.samples_out[(size_t)bglob * S + t] = x;
+                        if (p.labels_out) p.labels_out[(size_t)bglob * S + t] = arg;
+                    }
+                    x = __shfl_sync(0xffffffffu, x, 0);
+                    fx = __shfl_sync(0xffffffffu, fx, 0);
+                    const float xnext = fl < nf ? (p.forced_x ? fx : x) : 0.f;
+                    if (lane < CL) {
+                        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa(sb + SM_X + fl * 4, (uint32_t)lane)), "f"(xnext) : "memory");
+                        mbar_arrive_remote(mapa(bar0 + B_X * 8, (uint32_t)lane));
+                    }
+                    TICK(12);
+                    continue;
+                }
                 const float *lg = reinterpret_cast<const float *>(smem + SM_SAMP) + ((lane >> 2) * FPC + warp) * UPC + (lane & 3) * 16;
                 float v[16];
 #pragma unroll

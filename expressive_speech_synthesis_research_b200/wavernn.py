@@ -297,7 +297,8 @@ class WaveRNN(nn.Module):
                 raise ValueError("%s must have shape %s, got %s" % (what, shape, tuple(t.shape)))
             return t
 
-        u = dev(uniforms, (S, B), "uniforms")
+        n_u = 1 if self.mode == 'RAW' else self.n_classes // 3 + 1
+        u = dev(uniforms, (S, B) if n_u == 1 else (S, B, n_u), "uniforms")
         fx = dev(forced_x, (S, B), "forced_x")
         if seed is None:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())

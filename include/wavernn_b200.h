@@ -52,7 +52,7 @@ typedef struct {
                             WRNN_PREC_BF16_DENSE: the dense-regime kernel (north star: "tcgen05 tensor-core tiles when
                             the fold batch makes the per-step matmul dense"): bf16 weights streamed from L2 by TMA,
                             bf16 activations, fp32 accumulation in tensor memory, fp32 recurrent state and sampling;
-                            clusters of 8 CTAs advance 32 folds each, 500+ folds in flight per GPU.  RAW 512 classes. */
+                            clusters of 8 CTAs advance 32 folds each, 480 folds in flight per GPU.  RAW with 512 classes, or MOL. */
 } wrnn_config;
 
 /* The sixteen state_dict tensors on the step path, torch [out, in] row-major fp32, HOST memory

@@ -26,9 +26,9 @@ def bf16_round(a):
 
 
 class DenseReplay:
-    def __init__(self, sd):
+    def __init__(self, sd, mode="RAW"):
         C = sd["fc3.weight"].shape[0]
-        cfg = _lib.Config(512, 512, 80, 32, C, _lib.MODE["RAW"], _lib.PRECISION["bf16-dense"])
+        cfg = _lib.Config(512, 512, 80, 32, C, _lib.MODE[mode], _lib.PRECISION["bf16-dense"])
         L = _lib.lib()
         lay = (ctypes.c_int64 * 8)()
         _lib.check(L.wrnn_dense_layout(ctypes.byref(cfg), lay))
@@ -139,7 +139,9 @@ class DenseReplay:
                     elif cm == C_F2:
                         images[3][sl] = rnd(np.maximum(acc[rank][D_F2][:UPC] + sv[B4][:, None], 0))
                     elif cm == C_F3:
-                        out[t, :, sl] = (acc[rank][D_F3][:UPC] + sv[B5][:, None]).T
+                        lo, hi = UPC * rank, min(UPC * rank + UPC, self.C)          # MOL: only rows 0-29 of CTA 0 exist
+                        if hi > lo:
+                            out[t, :, lo:hi] = (acc[rank][D_F3][:hi - lo] + sv[B5][:hi - lo, None]).T
                 if cm == C_G2:
                     images[1] = rnd(h2)
                 if cm == C_F3:

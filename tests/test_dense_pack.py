@@ -14,14 +14,14 @@ TOL_DENSE_WEIGHTS_ONLY = 3e-3      # bf16 weights (rounded after the fp64 foldin
 TOL_DENSE = 5e-3                   # bf16 weights and bf16 activations / conditioning (what the kernel computes)
 
 
-def _case(seed=5, B=5, S=6):
-    sd = synth.make_state("RAW", "ref", 3)
+def _case(seed=5, B=5, S=6, mode="RAW"):
+    sd = synth.make_state(mode, "ref", 3)
     rng = np.random.default_rng(seed)
     mels = rng.uniform(0, 1, (B, S, 80)).astype(np.float32)
     aux = rng.normal(0, 1, (B, S, 128)).astype(np.float32)
     forced = rng.uniform(-1, 1, (S, B)).astype(np.float32)
-    U = np.zeros((S, B), np.float32) + 0.5
-    want = c_oracle.generate_folds(sd, "RAW", mels, aux, U, forced_x=forced, want_logits=True, precision="fp64")["logits"]
+    U = np.zeros((S, B) if mode == "RAW" else (S, B, 11), np.float32) + 0.5
+    want = c_oracle.generate_folds(sd, mode, mels, aux, U, forced_x=forced, want_logits=True, precision="fp64")["logits"]
     return sd, mels, aux, forced, want
 
 
@@ -52,11 +52,15 @@ def test_dense_stream_reproduces_oracle_logits_with_exact_activations():
     assert 1e-7 < err < TOL_DENSE_WEIGHTS_ONLY, err
 
 
-def test_dense_stream_with_bf16_activations_within_tolerance():
-    sd, mels, aux, forced, want = _case()
-    got = DenseReplay(sd).run(mels.astype(np.float64), aux.astype(np.float64), forced, round_act=True)
+@pytest.mark.parametrize("mode", ["RAW", "MOL"])
+def test_dense_stream_with_bf16_activations_within_tolerance(mode):
+    sd, mels, aux, forced, want = _case(mode=mode)
+    got = DenseReplay(sd, mode).run(mels.astype(np.float64), aux.astype(np.float64), forced, round_act=True)
     err = np.abs(got - want).max()
     assert err < TOL_DENSE, err
+    if mode == "MOL":
+        assert got.shape[-1] == 30
+        return
     # the approximation must not change what is sampled in any material way: softmax distributions stay close
     p = lambda lg: np.exp(lg - lg.max(-1, keepdims=True)) / np.exp(lg - lg.max(-1, keepdims=True)).sum(-1, keepdims=True)
     tv = 0.5 * np.abs(p(got) - p(want)).sum(-1).max()
@@ -66,5 +70,5 @@ def test_dense_stream_with_bf16_activations_within_tolerance():
 def test_dense_rejects_unsupported_configs():
     L = _lib.lib()
     lay = (ctypes.c_int64 * 8)()
-    for cfg in (_lib.Config(512, 512, 80, 32, 30, 1, 2), _lib.Config(512, 512, 80, 32, 256, 0, 2)):
+    for cfg in (_lib.Config(512, 512, 80, 32, 30, 0, 2), _lib.Config(512, 512, 80, 32, 256, 0, 2), _lib.Config(512, 512, 80, 32, 512, 1, 2)):
         assert L.wrnn_dense_layout(ctypes.byref(cfg), lay) != 0

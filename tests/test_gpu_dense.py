@@ -171,3 +171,43 @@ def test_dense_in_kernel_conditioning_expansion_matches_the_materialised_path():
     assert np.abs(out[True] - want).max() <= TOL_DENSE_LOGITS
     # unbatched: one fold over the whole utterance
     m.generate(synth.make_mel(22, seed=11), False, target, overlap, True, seed=1)
+
+
+def _mol_from_logits(logits, U):
+    """sample_from_discretized_mix_logistic (utility/distribution.py:87-123) in float32 from given logits [S,B,30], U [S,B,11]."""
+    lg = logits.astype(np.float32)
+    u1 = (1e-5 + ((1.0 - 1e-5) - 1e-5) * U[..., :10].astype(np.float64)).astype(np.float32)
+    score = lg[..., :10] - np.log(-np.log(u1))
+    arg = score.argmax(-1)
+    mean = np.take_along_axis(lg[..., 10:20], arg[..., None], -1)[..., 0]
+    ls = np.maximum(np.take_along_axis(lg[..., 20:30], arg[..., None], -1)[..., 0], np.float32(-32.23619130191664))
+    u2 = (1e-5 + ((1.0 - 1e-5) - 1e-5) * U[..., 10].astype(np.float64)).astype(np.float32)
+    x = mean + np.exp(ls) * (np.log(u2) - np.log(np.float32(1.0) - u2))
+    return np.clip(x, -1, 1).astype(np.float32), arg
+
+
+def test_dense_mol_logits_and_sampling():
+    """MOL on the dense kernel: the 30 outputs are rows 0-29 of CTA 0's fc3 tile.  Teacher-forced logits vs the fp64 oracle within the
+    bf16 tolerance; every sample is the mixture-of-logistics draw of the kernel's OWN logits (same mixture, value within 1e-5)."""
+    m = WaveRNN(**synth.model_kwargs("MOL", "ref"))
+    sd = synth.make_state("MOL", "ref", 0)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m.precision = "bf16-dense"
+    B, S = 37, 40
+    rng = np.random.default_rng(51)
+    mels = rng.uniform(0, 1, (B, S, 80)).astype(np.float32)
+    aux = rng.normal(0, 1, (B, S, 128)).astype(np.float32)
+    U = rng.uniform(0, 1, (S, B, 11)).astype(np.float32)
+    forced = rng.uniform(-1, 1, (S, B)).astype(np.float32)
+    r = run_folds(m, mels, aux, U, forced=forced, logits=True)
+    want = c_oracle.generate_folds(sd, "MOL", mels, aux, U, forced_x=forced, want_logits=True, precision="fp64")["logits"]
+    assert r["logits"].shape == want.shape == (S, B, 30)
+    assert np.abs(r["logits"] - want).max() <= TOL_DENSE_LOGITS
+    r = run_folds(m, mels, aux, U, logits=True)                       # free running
+    x, arg = _mol_from_logits(r["logits"], U)
+    assert np.array_equal(arg.T, r["labels"])
+    assert np.abs(x.T - r["samples"]).max() <= 1e-5
+    mel = synth.make_mel(40, seed=4)                                  # generate(): frames mode, Philox draws
+    wav = m.generate(mel, True, 1000, 100, True, seed=3)
+    assert wav.shape == (39 * 200,) and np.isfinite(wav).all() and np.abs(wav).max() <= 1.0
