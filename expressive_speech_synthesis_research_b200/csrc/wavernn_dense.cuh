@@ -704,7 +704,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                     // sample_from_discretized_mix_logistic (utility/distribution.py:87-123) as in the fp32 kernel: the 30 outputs are
                     // rows 0-29 of CTA 0's tile; lane i < 10 scores mixture i (Gumbel-max), lane 0 draws from the chosen logistic
                     const float *l30 = reinterpret_cast<const float *>(smem + SM_SAMP) + warp * UPC;     // source CTA 0, fold `warp`
-                    if (p.logits_out && fl < nf && lane < MOL_C) p.logits_out[((size_t)t * p.B + bglob) * MOL_C + lane] = l30[lane];
+                    const float my_logit = lane < MOL_C ? l30[lane] : 0.f;
                     float best = -INFINITY;
                     int arg = 1 << 20;
                     if (lane < MOL_NR) {
@@ -730,8 +730,6 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                         const float u2 = (float)(1e-5 + ((1.0 - 1e-5) - 1e-5) * (double)u2r);
                         x = mean + expf(ls) * (logf(u2) - logf(1.0f - u2));
                         x = fminf(fmaxf(x, -1.0f), 1.0f);
-                        p.samples_out[(size_t)bglob * S + t] = x;
-                        if (p.labels_out) p.labels_out[(size_t)bglob * S + t] = arg;
                     }
                     x = __shfl_sync(0xffffffffu, x, 0);
                     fx = __shfl_sync(0xffffffffu, fx, 0);
@@ -740,6 +738,11 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                         asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa(sb + SM_X + fl * 4, (uint32_t)lane)), "f"(xnext) : "memory");
                         mbar_arrive_remote(mapa(bar0 + B_X * 8, (uint32_t)lane));
                     }
+                    if (lane == 0 && fl < nf) {
+                        p.samples_out[(size_t)bglob * S + t] = x;
+                        if (p.labels_out) p.labels_out[(size_t)bglob * S + t] = arg;
+                    }
+                    if (p.logits_out && fl < nf && lane < MOL_C) p.logits_out[((size_t)t * p.B + bglob) * MOL_C + lane] = my_logit;
                     TICK(12);
                     continue;
                 }
@@ -750,11 +753,9 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                     const float4 qv = *reinterpret_cast<const float4 *>(lg + j);
                     v[j] = qv.x; v[j + 1] = qv.y; v[j + 2] = qv.z; v[j + 3] = qv.w;
                 }
-                if (p.logits_out && fl < nf) {
-                    float *dst = p.logits_out + ((size_t)t * p.B + bglob) * NCLASS + lane * 16;
+                float lgv[16];                                  // the raw logits, written out (if asked for) after the feedback is on its way
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
+                for (int j = 0; j < 16; ++j) lgv[j] = v[j];
                 float m = v[0];
 #pragma unroll
                 for (int j = 1; j < 16; ++j) m = fmaxf(m, v[j]);
@@ -784,14 +785,21 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                 for (int off = 16; off >= 1; off >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, off);
                 const int kk = cnt > NCLASS - 1 ? NCLASS - 1 : cnt;
                 const float sample = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, (float)kk), (float)NCLASS - 1.0f), 1.0f);   // :214
+                const float xnext = fl < nf ? (p.forced_x ? fx : sample) : 0.f;
+                // the feedback first: the release that follows the remote store is a full memory barrier for the thread, so the global
+                // stores of the outputs are issued after it, not before
+                if (lane < CL) {                                // lane d delivers x to CTA d
+                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa(sb + SM_X + fl * 4, (uint32_t)lane)), "f"(xnext) : "memory");
+                    mbar_arrive_remote(mapa(bar0 + B_X * 8, (uint32_t)lane));
+                }
                 if (lane == 0 && fl < nf) {
                     p.samples_out[(size_t)bglob * S + t] = sample;
                     if (p.labels_out) p.labels_out[(size_t)bglob * S + t] = kk;
                 }
-                const float xnext = fl < nf ? (p.forced_x ? fx : sample) : 0.f;
-                if (lane < CL) {                                // lane d delivers x to CTA d
-                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa(sb + SM_X + fl * 4, (uint32_t)lane)), "f"(xnext) : "memory");
-                    mbar_arrive_remote(mapa(bar0 + B_X * 8, (uint32_t)lane));
+                if (p.logits_out && fl < nf) {
+                    float *dst = p.logits_out + ((size_t)t * p.B + bglob) * NCLASS + lane * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(lgv[j], lgv[j + 1], lgv[j + 2], lgv[j + 3]);
                 }
                 TICK(12);
             }
