@@ -159,6 +159,12 @@ __device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, uint32_t src_c
 {
     asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
 }
+// remote 4-byte store that completes 4 bytes of the destination CTA's mbarrier transaction count: no release fence on the sender
+// (mbarrier.arrive.release.cluster costs a MEMBAR.ALL.GPU), no cluster-scope acquire on the receiver
+__device__ __forceinline__ void st_async_remote(uint32_t dst_cluster, float v, uint32_t bar_cluster)
+{
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst_cluster), "r"(__float_as_uint(v)), "r"(bar_cluster) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -429,7 +435,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
         }
         for (int i = 0; i < 4; ++i) mbar_init(bar0 + (B_ACT + i) * 8, 1);
         mbar_init(bar0 + B_LG * 8, 1);
-        mbar_init(bar0 + B_X * 8, CL * FPC);
+        mbar_init(bar0 + B_X * 8, 1);
         mbar_init(bar0 + B_COND * 8, NEPI / 32);
         for (int i = 0; i < 5; ++i) mbar_init(bar0 + (B_ACC + i) * 8, 1);
         mbar_init(bar0 + B_DONE * 8, 1);
@@ -594,6 +600,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
         if (FRAMES) cond_load_frames(p, geo, nf, tid, 1, cst, cr);
         else cond_load(p, geo, nf, tid, 1, cr);
 
+        if (tid == 0) mbar_expect_tx(bar0 + B_X * 8, BC * 4);   // the 32 samples of step 0 (one st.async of 4 bytes per fold)
         unsigned ph = 0;                                        // phase bits of B_ACC + {0..4}, B_X (bit 5), B_LG (bit 6)
         bool ok = true;
         long long pe[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tk = clock64();
@@ -606,9 +613,10 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             if (!ok) break;
             TICK(0);
             if (t > 0) {
-                ok = mbar_wait<true>(bar0 + B_X * 8, (ph >> 5) & 1u, p.status, 25);
+                ok = mbar_wait(bar0 + B_X * 8, (ph >> 5) & 1u, p.status, 25);
                 ph ^= 1u << 5;
                 if (!ok) break;
+                if (tid == 0) mbar_expect_tx(bar0 + B_X * 8, BC * 4);   // arm the next step's phase
             }
             TICK(5);
             tc_fence_after();
@@ -735,8 +743,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                     fx = __shfl_sync(0xffffffffu, fx, 0);
                     const float xnext = fl < nf ? (p.forced_x ? fx : x) : 0.f;
                     if (lane < CL) {
-                        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa(sb + SM_X + fl * 4, (uint32_t)lane)), "f"(xnext) : "memory");
-                        mbar_arrive_remote(mapa(bar0 + B_X * 8, (uint32_t)lane));
+                        st_async_remote(mapa(sb + SM_X + fl * 4, (uint32_t)lane), xnext, mapa(bar0 + B_X * 8, (uint32_t)lane));
                     }
                     if (lane == 0 && fl < nf) {
                         p.samples_out[(size_t)bglob * S + t] = x;
@@ -789,8 +796,7 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                 // the feedback first: the release that follows the remote store is a full memory barrier for the thread, so the global
                 // stores of the outputs are issued after it, not before
                 if (lane < CL) {                                // lane d delivers x to CTA d
-                    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(mapa(sb + SM_X + fl * 4, (uint32_t)lane)), "f"(xnext) : "memory");
-                    mbar_arrive_remote(mapa(bar0 + B_X * 8, (uint32_t)lane));
+                    st_async_remote(mapa(sb + SM_X + fl * 4, (uint32_t)lane), xnext, mapa(bar0 + B_X * 8, (uint32_t)lane));
                 }
                 if (lane == 0 && fl < nf) {
                     p.samples_out[(size_t)bglob * S + t] = sample;
