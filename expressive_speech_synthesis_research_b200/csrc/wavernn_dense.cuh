@@ -492,14 +492,16 @@ __device__ __forceinline__ void dense_body(const DParams &p)
             }
         }
     } else if (warp == MMA_WARP) {
-        // ===== MMA issue: the whole warp walks the bundle table once per step (warp-uniform control flow and operands, so the
-        // descriptors live in uniform registers); one elected lane issues.  t = -1 primes the accumulators of step 0
-        {
-            const bool leader = elect_one();
+        // ===== MMA issue.  One elected lane runs the whole role: inside an elect.sync region ptxas keeps descriptors and loop state
+        // on the uniform datapath (a plain `lane == 0` test costs a register->uniform waterfall per product).  The tensor pipe holds
+        // next to nothing in flight, so whatever the issuing thread does between two products idles the pipe (scripts/umma_issue.cu:
+        // 40 cycles per product back to back, +285 cycles per bundle when every bundle re-enters the elect region, +170 like this).
+        // t = -1 runs the same table on zero images and primes the accumulators of step 0.
+        if (elect_one()) {
             unsigned ph_full = 0, ph_wait = 0;                  // phase bits: ring slots / wait events
             long long gb = 0;
             bool ok = true;
-            long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_step = 0;
+            long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             const long long t_begin = clock64();
             for (int t = -1; t < S && ok; ++t) {
                 const bool pre = t < 0;
@@ -523,53 +525,38 @@ __device__ __forceinline__ void dense_body(const DParams &p)
                     if (!ok) break;
                     tc_fence_after();
                     const uint32_t slot_base = sb + SM_RING + slot * SLOT;
-                    // one elected lane issues the whole bundle: inside an elect.sync region the compiler keeps descriptors and
-                    // loop state in uniform registers (a plain `lane == 0` test costs a register->uniform move per operand per MMA)
-                    if (elect_one()) {
-                        const int nseg = bd.nseg;
-                        for (int s = 0; s < nseg; ++s) {
-                            const Seg sg = bd.seg[s];
-                            const uint32_t rows = sg.rows, d = tmem + sg.dcol;
-                            const uint32_t IDESC = rows == 64 ? IDESC64 : IDESC128;
-                            uint32_t a_lo = smem_desc_lo(slot_base + (uint32_t)sg.off16 * 16, rows * 16);
-                            uint32_t b_lo = smem_desc_lo(sb + SM_IMG + (uint32_t)sg.bsrc16 * 16, CHUNK_B);
-                            const uint32_t a_inc = rows * 2;                  // one k-step = 2 chunks of rows x 16 B, in 16-byte units
-                            constexpr uint32_t b_inc = 2 * CHUNK_B / 16;
-                            tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, sg.first ? 0u : 1u);
-                            const int nk = sg.nk;
+                    const int nseg = bd.nseg;
+                    for (int s = 0; s < nseg; ++s) {
+                        const Seg sg = bd.seg[s];
+                        const uint32_t rows = sg.rows, d = tmem + sg.dcol;
+                        const uint32_t IDESC = rows == 64 ? IDESC64 : IDESC128;
+                        uint32_t a_lo = smem_desc_lo(slot_base + (uint32_t)sg.off16 * 16, rows * 16);
+                        uint32_t b_lo = smem_desc_lo(sb + SM_IMG + (uint32_t)sg.bsrc16 * 16, CHUNK_B);
+                        const uint32_t a_inc = rows * 2;                  // one k-step = 2 chunks of rows x 16 B, in 16-byte units
+                        constexpr uint32_t b_inc = 2 * CHUNK_B / 16;
+                        tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, sg.first ? 0u : 1u);
+                        const int nk = sg.nk;
 #pragma unroll 4
-                            for (int k = 1; k < nk; ++k) {
-                                a_lo += a_inc;
-                                b_lo += b_inc;
-                                tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, 1u);
-                            }
-                        }
-                        const int c = bd.commit;
-                        tc_commit(bar0 + (B_EMPTY + slot) * 8);
-                        if (c == C_H2RD) tc_commit(bar0 + B_H2RD * 8);
-                        else if (c != C_NONE && (c == C_G1 || !pre)) tc_commit(bar0 + (B_ACC + (c == C_G1 ? 0 : c)) * 8);
-                    }
-                    __syncwarp();
-                    if (PROF) {
-                        const long long t3 = clock64();
-                        pf[6] += t3 - t2;
-                        if (t == 10 && p.prof && leader) {
-                            if (b == 0) t_step = t1;
-                            long long *tr = p.prof + (size_t)blockIdx.x * PROF_N + 32 + b * 4;
-                            tr[0] = t1 - t_step;
-                            tr[1] = t2 - t_step;
-                            tr[2] = t3 - t_step;
+                        for (int k = 1; k < nk; ++k) {
+                            a_lo += a_inc;
+                            b_lo += b_inc;
+                            tc_mma(d, a_lo, b_lo, DESC_HI, IDESC, 1u);
                         }
                     }
+                    const int c = bd.commit;
+                    tc_commit(bar0 + (B_EMPTY + slot) * 8);
+                    if (c == C_H2RD) tc_commit(bar0 + B_H2RD * 8);
+                    else if (c != C_NONE && (c == C_G1 || !pre)) tc_commit(bar0 + (B_ACC + (c == C_G1 ? 0 : c)) * 8);
+                    if (PROF) pf[6] += clock64() - t2;
                 }
             }
-            if (leader) tc_commit(bar0 + B_DONE * 8);
-            __syncwarp();
+            tc_commit(bar0 + B_DONE * 8);
             mbar_wait(bar0 + B_DONE * 8, 0, p.status, 3);
             pf[7] = clock64() - t_begin;
-            if (PROF && p.prof && leader)
+            if (PROF && p.prof)
                 for (int i = 0; i < 8; ++i) p.prof[(size_t)blockIdx.x * PROF_N + i] = pf[i];
         }
+        __syncwarp();
     } else {
         // ===== epilogue warps =====
         const int q = warp & 3;
