@@ -5,9 +5,10 @@
 // Work split.  A thread-block cluster of CL = 8 CTAs owns up to BC = 32 folds for all their steps; there is no
 // grid-level synchronisation (clusters are independent, so a launch may hold more clusters than fit at once).
 // CTA `rank` of a cluster owns hidden units [64 rank, 64 rank + 64) of rnn1, rnn2, fc1, fc2 and classes
-// [64 rank, +64) of fc3.  Per step it multiplies its weight rows (MMA operand A, M = 128 rows, K-major, no swizzle)
-// with the activations of ALL 512 units of the cluster's folds (operand B, N = 32 folds, K-major), which every CTA
-// keeps as bf16 images in shared memory:  image byte (k, f) = (k / 8) * 512 + f * 16 + (k % 8) * 2.
+// [64 rank, +64) of fc3 (MOL: the 30 outputs are rows 0-29 of rank 0).  Per step it multiplies its weight rows (MMA operand A,
+// M = 128 for the [r | z] tiles, M = 64 for the n-gate and fc tiles, K-major, no swizzle) with the activations of ALL 512 units
+// of the cluster's folds (operand B, N = 32 folds, K-major), which every CTA keeps as bf16 images in shared memory:
+// image byte (k, f) = (k / 8) * 512 + f * 16 + (k % 8) * 2.
 // A CTA's freshly computed 64 units are a contiguous 4 KB block of such an image; it is written locally and
 // broadcast to the 7 peers with cp.async.bulk shared::cta -> shared::cluster, completing on the peers' mbarriers.
 //
@@ -54,7 +55,7 @@ enum { DV_B1R = 0, DV_U1R, DV_B1Z, DV_U1Z, DV_B1NI, DV_U1N, DV_B1NH, DV_B2R, DV_
 
 struct Seg {
     uint16_t off16;    // byte offset of the A tile in the ring slot / 16
-    uint16_t rows;     // valid rows of the A tile (64 or 128); rows beyond alias the following bytes and feed unused lanes
+    uint16_t rows;     // rows of the A tile: 128 -> M = 128 product, 64 -> M = 64 product
     uint16_t nk;       // k-steps of 16
     uint16_t bsrc16;   // B operand: byte offset from the first activation image / 16
     uint16_t dcol;     // accumulator column
