@@ -492,6 +492,7 @@ static int32_t pack_dense(int C, const wrnn_weights *w, DensePack &out)
     fc(W_NONE, C_NONE, IMG_H1, w->fc1_w, RA, D_F1, 0, false);
     one(W_COND, C_NONE, {DenseSeg(128, 7, cnd(0), D_G1_T0, 1, [=](int rank, int m, int k) { return g1[(size_t)rowT0(rank, m) * KC + k]; })});
     one(W_NONE, C_NONE, {DenseSeg(UPC, 7, cnd(0), D_G1_1I, 1, [=](int rank, int m, int k) { return g1[(size_t)rowN(rank, m) * KC + k]; })});
+    t1_half(C_NONE, IMG_H1, w->r1_whh, R, D_G1_1H, 0, 1);       // one sixth of Whh1.h1(t) here, the rest in the tail of (d)
     // (b) critical: Wfc1x.h2(t) -> f1.  Inside E3 + the y1 exchange: P2.c(t+1) -> g2 (first touch; E2(t) has drained g2)
     fc(W_H2, C_F1, IMG_H2, w->fc1_w, RA, D_F1, 0, false);
     one(W_NONE, C_NONE, {DenseSeg(128, 8, cnd(0), D_G2_T0, 1, [=](int rank, int m, int k) { return p2(rowT0(rank, m), k); })});
@@ -509,7 +510,8 @@ static int32_t pack_dense(int C, const wrnn_weights *w, DensePack &out)
     // [commit G1: E1(t+1) may start], then Whh2.h2(t) -> g2 [commit H2RD: this CTA no longer reads the h2(t) image]
     fc(W_Y2, C_F3, IMG_Y2, w->fc3_w, R, D_F3, 1, true);
     one(W_NONE, C_NONE, {DenseSeg(UPC, 2, cnd(22), D_F2, 1, [=](int rank, int m, int k) { return (double)f2[(size_t)unit(rank, m) * RA + R + k]; })});
-    hidden(W_NONE, C_G1, IMG_H1, w->r1_whh, R, D_G1_T0, D_G1_1H, 0, 1);
+    for (int kb = 0; kb < 4; ++kb) t0_block(C_NONE, IMG_H1, w->r1_whh, R, D_G1_T0, kb, 0);
+    t1_half(C_G1, IMG_H1, w->r1_whh, R, D_G1_1H, 1, 0);
     t0_block(C_NONE, IMG_H2, w->r2_whh, R, D_G2_T0, 2, 0);
     t0_block(C_NONE, IMG_H2, w->r2_whh, R, D_G2_T0, 3, 0);
     t1_half(C_H2RD, IMG_H2, w->r2_whh, R, D_G2_1H, 1, 0);
