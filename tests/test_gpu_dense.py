@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_DENSE_LOGITS = 5e-3
 TOL_DENSE_CDF = 1e-5
-DENSE_LABEL_SLACK = 4
+DENSE_LABEL_SLACK = 2
 
 _M = {}
 
@@ -80,7 +80,7 @@ def test_dense_free_running_is_consistent_with_the_oracle():
     assert np.abs(r["logits"] - o["logits"]).max() <= TOL_DENSE_LOGITS
     d = np.abs(o["labels"].astype(np.int64) - r["labels"].astype(np.int64))
     assert d.max() <= DENSE_LABEL_SLACK, d.max()
-    assert (d == 0).mean() > 0.6, (d == 0).mean()
+    assert (d == 0).mean() > 0.98, (d == 0).mean()                 # measured 99.6 % equal, the rest off by one level
 
 
 def test_dense_pooling_chunking_and_placement_do_not_change_a_fold():
