@@ -221,6 +221,11 @@ def dense_regime(args, dev, state, pk):
 # this repo's CUDA path
 # ------------------------------------------------------------------------------------------------
 def run_b200(args):
+    # stdout carries exactly one JSON line: anything a library prints there meanwhile (NCCL announces its version on stdout when
+    # the first communicator is created) goes to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from expressive_speech_synthesis_research_b200 import WaveRNN
@@ -357,7 +362,8 @@ def run_b200(args):
             except Exception as e:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": "failed: %r" % (e,)}
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
