@@ -211,3 +211,10 @@ def test_dense_mol_logits_and_sampling():
     mel = synth.make_mel(40, seed=4)                                  # generate(): frames mode, Philox draws
     wav = m.generate(mel, True, 1000, 100, True, seed=3)
     assert wav.shape == (39 * 200,) and np.isfinite(wav).all() and np.abs(wav).max() <= 1.0
+
+
+def test_dense_edge_cases_fold_counts_and_short_runs():
+    """Fold counts around the cluster (32) and wave (480) boundaries, runs of 1-3 steps (the conditioning prefetch reaches past the
+    end), the shortest legal utterance through generate(): no watchdog, finite logits, labels consistent with the kernel's logits."""
+    from scripts import dense_edge_sweep
+    assert dense_edge_sweep.main() == 0
