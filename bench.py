@@ -210,7 +210,11 @@ def dense_regime(args, dev, state, pk):
     tf = d["fold_steps_per_us"] * 1e6 * FLOP_PER_FOLD_STEP["RAW"] / 1e12
     out["speedup_vs_fp32_kernel"] = d["fold_steps_per_us"] / out["fp32"]["fold_steps_per_us"]
     out["roofline"] = {"bound": "tensor", "kernel": "wavernn_dense_kernel", "achieved": tf, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                       "frac": tf / pk["bf16_tflops"], "traffic": None,
+                       "frac": tf / pk["bf16_tflops"],
+                       # ncu --set full of this kernel at 480 folds x 300 steps: dram read 127.8 MB + write 4.1 MB (profiles/r01_dense.md
+                       # section 3; algorithmic 832 B per fold-step = 119.8 MB), scaled to this launch's fold-steps
+                       "traffic": (127.8e6 + 4.1e6) / (480 * 300) * d["folds"] * args.dense_steps if d["folds"] == 480 else None,
+                       "traffic_unit": "dram bytes per launch (ncu capture of 480 x 300, scaled by fold-steps)",
                        "note": "algorithmic FLOPs (8.14 MFLOP per fold-step); every tcgen05.mma is M=128 x N=32 x K=16 and is paced by "
                                "its shared-memory operand reads (40 clk measured, scripts/umma_rate.cu), the step by the shared-memory "
                                "port (weights cross it twice: TMA fill + MMA read) and the cluster exchange (DESIGN.md 9)"}
@@ -322,6 +326,12 @@ def run_b200(args):
         lat_floor = 5 * t_sync if t_sync else None
         fma_floor = wl["folds"] * FLOP_PER_FOLD_STEP[args.mode] / (fp32_peak * 1e12) * 1e6
         dense = args.precision == "bf16-dense"
+        # dram__bytes_read.sum + dram__bytes_write.sum of the one ncu --set full capture of this kernel on this workload
+        # (20 folds x 3000 steps of configs[1]: 66.2 MB + 3.8 MB, profiles/r01_summary.md section 3), scaled to this launch's
+        # fold-steps; other modes / kernels have no capture of their own and report null
+        traffic = None
+        if not dense and args.precision == "fp32" and args.mode == "RAW" and wl["folds"] == 20:
+            traffic = (66.2e6 + 3.8e6) / (20 * 3000) * fold_steps
         line = {
             "metric": "generated_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": n,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3,
@@ -336,8 +346,9 @@ def run_b200(args):
             "gpu_launches": int((info1.launches - info0.launches) + (info1.epilogue_launches - info0.epilogue_launches)),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "wavernn_dense_kernel" if dense else "wavernn_persistent_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk_src,
-                         "kernel_ms_per_launch": k_ms,
+                         "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk_src,
+                         "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                         "traffic_unit": "bytes per launch (ncu dram read + write of a 20 x 3000 capture, scaled by fold-steps)",
                          "note": "HBM is not what bounds this kernel (840 B per fold-step, measured dram traffic ~0.7 GB/s); "
                                  "the binding terms are the step-latency model below (SURVEY.md 8d, DESIGN.md 7): five "
                                  "dependent grid-level exchanges per step plus the FFMA2 / shared-memory floors"},
