@@ -8,6 +8,7 @@ i32, i64, u64, vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_vo
 
 MODE = {"RAW": 0, "MOL": 1}
 PRECISION = {"fp32": 0, "bf16": 1, "bf16-dense": 2}
+ABI_VERSION = 2
 
 
 class Config(ctypes.Structure):
@@ -28,7 +29,7 @@ class Info(ctypes.Structure):
     _fields_ = [("ctas", i32), ("threads", i32), ("smem_bytes", i32), ("folds_per_group", i32),
                 ("max_folds_per_launch", i32), ("exchanges_per_step", i32), ("sm_count", i32),
                 ("launches", i64), ("epilogue_launches", i64), ("last_kernel_status", i32),
-                ("last_kernel_ms", ctypes.c_float)]
+                ("last_kernel_ms", ctypes.c_float), ("kernel_kind", i32)]
 
 
 # every symbol include/wavernn_b200.h declares: name -> (restype, argtypes)
@@ -40,6 +41,8 @@ SYMBOLS = {
     "wrnn_load_weights": (i32, [vp, ctypes.POINTER(Weights)]),
     "wrnn_packed_floats": (i64, [ctypes.POINTER(Config)]),
     "wrnn_pack_weights_host": (i32, [ctypes.POINTER(Config), ctypes.POINTER(Weights), vp, i64]),
+    "wrnn_wide_packed_floats": (i64, [ctypes.POINTER(Config), ctypes.POINTER(i64)]),
+    "wrnn_wide_pack_host": (i32, [ctypes.POINTER(Config), ctypes.POINTER(Weights), vp, i64]),
     "wrnn_dense_layout": (i32, [ctypes.POINTER(Config), ctypes.POINTER(i64)]),
     "wrnn_dense_pack_host": (i32, [ctypes.POINTER(Config), ctypes.POINTER(Weights), vp, vp, vp]),
     "wrnn_fold_index": (i32, [i64, i64, i64, ctypes.POINTER(i64), ctypes.POINTER(i64)]),
@@ -47,6 +50,8 @@ SYMBOLS = {
     "wrnn_generate_folds_frames": (i32, [vp, vp, i64, vp, i64, vp, i32, i32, vp, i32, i32, vp, u64, vp, vp, vp, vp, vp]),
     "wrnn_xfade_unfold": (i32, [vp, i32, i32, i32, i32, i32, i64, i32, vp, vp]),
     "wrnn_xfade_unfold_segment": (i32, [vp, i32, i32, i32, i32, i64, i32, i64, i64, i64, i64, vp, vp]),
+    "wrnn_synchronize": (i32, [vp]),
+    "wrnn_query": (i32, [vp, ctypes.POINTER(i32), ctypes.POINTER(i32)]),
     "wrnn_get_info": (i32, [vp, ctypes.POINTER(Info)]),
     "wrnn_set_profiling": (i32, [vp, i32]),
     "wrnn_get_stage_cycles": (i32, [vp, vp, i32]),
@@ -75,8 +80,8 @@ def lib():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)          # AttributeError if the .so lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if L.wrnn_abi_version() != 1:
-            raise WaveRNNLibraryError("ABI version mismatch: library %d, binding 1" % L.wrnn_abi_version())
+        if L.wrnn_abi_version() != ABI_VERSION:
+            raise WaveRNNLibraryError("ABI version mismatch: library %d, binding %d" % (L.wrnn_abi_version(), ABI_VERSION))
         _LIB = L
     return _LIB
 

@@ -3,7 +3,9 @@
 #include "../../include/wavernn_b200.h"
 #include "wavernn_kernel.cuh"
 #include "wavernn_dense.cuh"
+#include "wavernn_wide.cuh"
 
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -16,7 +18,7 @@
 using namespace wrnn;
 
 static thread_local std::string g_err;
-static long long g_epilogue_launches = 0;
+static std::atomic<long long> g_epilogue_launches{0};
 
 static int32_t fail(int32_t code, const char *fmt, ...)
 {
@@ -45,6 +47,8 @@ struct wrnn_handle {
     float *wimg = nullptr;
     unsigned long long *xb = nullptr;   // LL exchange buffers
     int *status = nullptr;
+    int *status_host = nullptr;      // pinned copy of `status`, filled by the D2H that closes every call
+    bool pending = false;            // a generate call has been enqueued and not yet waited for
     long long *fold_dev = nullptr;   // [2][fold_cap]
     int fold_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -53,13 +57,35 @@ struct wrnn_handle {
     float last_ms = 0.f;
     long long *prof_dev = nullptr;   // [NCTA][PROF_SLOTS], allocated by wrnn_set_profiling
     bool profiling = false;
+    // wide kernel (csrc/wavernn_wide.cuh): all folds of a launch through one exchange per stage; fp32 RAW-512 / MOL
+    int wide = 0, wide_nsamp = 0;
+    int last_kernel = 0;                  // 0 grouped (round-1) kernel, 1 wide kernel, 2 dense kernel
+    float *wide_img = nullptr;            // [NWORK][IMG_FLOATS]
+    unsigned *wide_xb = nullptr;          // XW_TOTAL words
+    int *progress_host = nullptr, *progress_dev = nullptr;   // mapped step counter (wrnn_progress)
     // precision bf16-dense (csrc/wavernn_dense.cuh): streamed operand tiles, bundle table, per-row fp32 vectors
     int dense = 0, dense_nb = 0, dense_clusters = 0;
     unsigned dense_stream_bytes = 0;
     unsigned char *dense_stream = nullptr;
     wrnn_dense::Bundle *dense_table = nullptr;
     float *dense_sv = nullptr;
-    long long *dense_prof = nullptr;       // [clusters * CL][PROF_N], development profiling
+    long long *dense_prof = nullptr;       // [CTAs of the launch][PROF_N], development profiling
+    size_t dense_prof_slots = 0;
+};
+
+// Every entry point that touches a device restores the caller's current device on return.
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
 };
 
 extern "C" int32_t wrnn_abi_version(void) { return WRNN_ABI_VERSION; }
@@ -125,6 +151,11 @@ static const void *persistent_kernel(int T, int model, int bf16w, int prof)
     return plain[model][bf16w ? 1 : 0][T - 1];
 }
 #undef K3
+static bool wide_supported(const wrnn_config &c)
+{
+    return c.precision == WRNN_PREC_FP32 && ((c.mode == WRNN_MODE_RAW && c.n_classes == 512) || (c.mode == WRNN_MODE_MOL && c.n_classes == 30));
+}
+
 static int model_of(const wrnn_config &c) { return c.mode == WRNN_MODE_MOL ? 2 : c.n_classes == 512 ? 1 : 0; }
 
 extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_handle **out)
@@ -136,7 +167,7 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
     int ndev = 0;
     CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (device < 0 || device >= ndev) return fail(WRNN_ERR_CUDA, "device %d not present (%d CUDA devices)", device, ndev);
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard_(device);
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(WRNN_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
@@ -180,6 +211,27 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
     H_TRY(cudaMalloc(&h->wimg, (size_t)NCTA * w_image_floats(rows5, h->bf16w) * sizeof(float)));
     H_TRY(cudaMalloc(&h->xb, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long) ));
     H_TRY(cudaMalloc(&h->status, 4 * sizeof(int)));
+    H_TRY(cudaHostAlloc(&h->status_host, 4 * sizeof(int), cudaHostAllocDefault));
+    memset(h->status_host, 0, 4 * sizeof(int));
+    H_TRY(cudaHostAlloc(&h->progress_host, sizeof(int), cudaHostAllocMapped));
+    *h->progress_host = 0;
+    H_TRY(cudaHostGetDevicePointer((void **)&h->progress_dev, h->progress_host, 0));
+    if (wide_supported(*cfg) && prop.multiProcessorCount > wrnn_wide::NWORK && wrnn_wide::SM_BYTES <= h->smem_limit) {
+        // the wide kernel: 128 worker CTAs + up to 20 sampler CTAs, one per SM (cooperative launch)
+        const void *wk[] = {(const void *)wrnn_wide::wavernn_wide_kernel, (const void *)wrnn_wide::wavernn_wide_kernel_mol,
+                            (const void *)wrnn_wide::wavernn_wide_kernel_prof, (const void *)wrnn_wide::wavernn_wide_kernel_mol_prof,
+                            (const void *)wrnn_wide::wavernn_wide_probe_kernel};
+        for (const void *k : wk) H_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, wrnn_wide::SM_BYTES));
+        int wocc = 0;
+        H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, wk[0], NTHREADS, wrnn_wide::SM_BYTES));
+        if (wocc >= 1) {
+            h->wide = 1;
+            h->wide_nsamp = prop.multiProcessorCount - wrnn_wide::NWORK;
+            if (h->wide_nsamp > wrnn_wide::MAXSAMP) h->wide_nsamp = wrnn_wide::MAXSAMP;
+            H_TRY(cudaMalloc(&h->wide_img, (size_t)wrnn_wide::NWORK * wrnn_wide::IMG_FLOATS * sizeof(float)));
+            H_TRY(cudaMalloc(&h->wide_xb, (size_t)wrnn_wide::XW_TOTAL * sizeof(unsigned)));
+        }
+    }
     H_TRY(cudaEventCreate(&h->ev0));
     H_TRY(cudaEventCreate(&h->ev1));
     if (cfg->precision == WRNN_PREC_BF16_DENSE) {
@@ -211,10 +263,15 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
 extern "C" void wrnn_destroy(wrnn_handle *h)
 {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceGuard guard_(h->device);
+    if (h->pending && h->ev1) cudaEventSynchronize(h->ev1);
     cudaFree(h->wimg);
     cudaFree(h->xb);
     cudaFree(h->status);
+    if (h->status_host) cudaFreeHost(h->status_host);
+    if (h->progress_host) cudaFreeHost(h->progress_host);
+    cudaFree(h->wide_img);
+    cudaFree(h->wide_xb);
     cudaFree(h->fold_dev);
     cudaFree(h->prof_dev);
     cudaFree(h->dense_stream);
@@ -346,6 +403,104 @@ static void pack_images(int C, int rows5, const wrnn_weights *w, std::vector<flo
         for (int r = 0; r < rows5; ++r) {
             const int cls = rows5 * c + r;
             sv[SV_B5 + r] = cls < C ? w->fc3_b[cls] : 0.f;
+        }
+    }
+}
+
+// ---- wide kernel images (csrc/wavernn_wide.cuh) --------------------------------------------------
+// Same algebra as pack_images (input layer folded in fp64, rounded once to fp32); different layouts:
+//   gate matrices  [warp 16][ig 4][ks 2][unit 4][ii 4][gate 3]   k = 32 warp + 2 (4 ig + ii) + ks
+//   fc matrices    [warp 16][q 4][ks 2][unit 4][e 4]             k = 32 warp + 2 (4 q + e) + ks
+//   conditioning   [k' 176][row block 8][4]: row block = which * 4 + unit, rows {P1 r, z, n, P3} (which 0) or
+//                  {P2 r, z, n, P4} (which 1); k' < 112: mel + a1 columns; [112, 144): a3 (which 0: the P3 row only) or
+//                  a2 (which 1: the P2 rows only); [144, 176): a4 (which 1: the P4 row only)
+static void pack_wide(int C, const wrnn_weights *w, std::vector<float> &img)
+{
+    using namespace wrnn_wide;
+    const int R = HID, F = 80, A = 32, KI = 1 + F + A, KC = F + A;
+    std::vector<double> Wc((size_t)R * KC), w0(R), bI(R);
+    for (int j = 0; j < R; ++j) {
+        w0[j] = w->I_w[(size_t)j * KI];
+        bI[j] = w->I_b[j];
+        for (int k = 0; k < KC; ++k) Wc[(size_t)j * KC + k] = w->I_w[(size_t)j * KI + 1 + k];
+    }
+    std::vector<double> G1, G2, G3, u1, u2, u3, c1, c2, c3;
+    gemm_f64(w->r1_wih, R, 3 * R, R, Wc, KC, G1);
+    gemm_f64(w->r2_wih, R + A, 3 * R, R, Wc, KC, G2);
+    gemm_f64(w->fc1_w, R + A, R, R, Wc, KC, G3);
+    gemm_f64(w->r1_wih, R, 3 * R, R, w0, 1, u1);
+    gemm_f64(w->r2_wih, R + A, 3 * R, R, w0, 1, u2);
+    gemm_f64(w->fc1_w, R + A, R, R, w0, 1, u3);
+    gemm_f64(w->r1_wih, R, 3 * R, R, bI, 1, c1);
+    gemm_f64(w->r2_wih, R + A, 3 * R, R, bI, 1, c2);
+    gemm_f64(w->fc1_w, R + A, R, R, bI, 1, c3);
+
+    img.assign((size_t)NWORK * IMG_FLOATS, 0.f);
+    for (int c = 0; c < NWORK; ++c) {
+        float *base = &img[(size_t)c * IMG_FLOATS];
+        const int j0 = UNITS * c;
+        auto gate_matrix = [&](int off, const float *M, int ld) {
+            for (int wp = 0; wp < 16; ++wp)
+                for (int ig = 0; ig < 4; ++ig)
+                    for (int ks = 0; ks < 2; ++ks)
+                        for (int u = 0; u < UNITS; ++u)
+                            for (int ii = 0; ii < 4; ++ii)
+                                for (int g = 0; g < 3; ++g) {
+                                    const int k = 32 * wp + 2 * (4 * ig + ii) + ks;
+                                    base[off + ((((wp * 4 + ig) * 2 + ks) * 4 + u) * 12) + ii * 3 + g] = M[(size_t)(j0 + u + R * g) * ld + k];
+                                }
+        };
+        gate_matrix(OFF_IH2, w->r2_wih, R + A);
+        gate_matrix(OFF_HH1, w->r1_whh, R);
+        gate_matrix(OFF_HH2, w->r2_whh, R);
+        auto fc_matrix = [&](int off, const float *M, int ld, int rows_valid) {
+            for (int wp = 0; wp < 16; ++wp)
+                for (int q = 0; q < 4; ++q)
+                    for (int ks = 0; ks < 2; ++ks)
+                        for (int u = 0; u < UNITS; ++u)
+                            for (int e = 0; e < 4; ++e) {
+                                const int k = 32 * wp + 2 * (4 * q + e) + ks, row = j0 + u;
+                                base[off + (((wp * 4 + q) * 2 + ks) * 4 + u) * 4 + e] = row < rows_valid ? M[(size_t)row * ld + k] : 0.f;
+                            }
+        };
+        fc_matrix(OFF_FC1, w->fc1_w, R + A, R);
+        fc_matrix(OFF_FC2, w->fc2_w, R + A, R);
+        fc_matrix(OFF_FC3, w->fc3_w, R, C);              // class = 4 * cta + unit (MOL: 30 rows, CTAs 0..7)
+        float *wc = base + OFF_WC;
+        for (int kp = 0; kp < KC2; ++kp)
+            for (int which = 0; which < 2; ++which)
+                for (int u = 0; u < UNITS; ++u) {
+                    float *dst = wc + (kp * 8 + which * 4 + u) * 4;
+                    const int row = j0 + u;
+                    for (int g = 0; g < 3; ++g) {
+                        double v = 0.0;
+                        if (kp < KC) v = which == 0 ? G1[(size_t)(row + R * g) * KC + kp] : G2[(size_t)(row + R * g) * KC + kp];
+                        else if (which == 1 && kp < KC + A) v = w->r2_wih[(size_t)(row + R * g) * (R + A) + R + (kp - KC)];   // a2
+                        dst[g] = (float)v;
+                    }
+                    double v = 0.0;
+                    if (which == 0) {                    // P3: G3 | a3
+                        if (kp < KC) v = G3[(size_t)row * KC + kp];
+                        else if (kp < KC + A) v = w->fc1_w[(size_t)row * (R + A) + R + (kp - KC)];
+                    } else if (kp >= KC + A) v = w->fc2_w[(size_t)row * (R + A) + R + (kp - KC - A)];       // P4: a4
+                    dst[3] = (float)v;
+                }
+        float *sv = base + OFF_SV;
+        for (int q = 0; q < 3; ++q)
+            for (int u = 0; u < UNITS; ++u) {
+                const int row = j0 + u + R * q;
+                sv[SV_U1 + q * 4 + u] = (float)u1[row];
+                sv[SV_B1 + q * 4 + u] = (float)(c1[row] + (double)w->r1_bih[row]);
+                sv[SV_BHH1 + q * 4 + u] = w->r1_bhh[row];
+                sv[SV_U2 + q * 4 + u] = (float)u2[row];
+                sv[SV_B2 + q * 4 + u] = (float)(c2[row] + (double)w->r2_bih[row]);
+                sv[SV_BHH2 + q * 4 + u] = w->r2_bhh[row];
+            }
+        for (int u = 0; u < UNITS; ++u) {
+            sv[SV_U3 + u] = (float)u3[j0 + u];
+            sv[SV_B3 + u] = (float)(c3[j0 + u] + (double)w->fc1_b[j0 + u]);
+            sv[SV_B4 + u] = w->fc2_b[j0 + u];
+            sv[SV_B5 + u] = j0 + u < C ? w->fc3_b[j0 + u] : 0.f;
         }
     }
 }
@@ -636,13 +791,37 @@ extern "C" int32_t wrnn_pack_weights_host(const wrnn_config *cfg, const wrnn_wei
     return WRNN_OK;
 }
 
+extern "C" int64_t wrnn_wide_packed_floats(const wrnn_config *cfg, int64_t *layout)
+{
+    int rows5, nprod5, n_u;
+    if (!cfg || derive_layout(*cfg, rows5, nprod5, n_u) || !wide_supported(*cfg)) return -1;
+    using namespace wrnn_wide;
+    if (layout) {
+        const int64_t v[8] = {IMG_FLOATS, OFF_IH2, OFF_HH1, OFF_HH2, OFF_FC1, OFF_FC2, OFF_FC3, OFF_WC};
+        memcpy(layout, v, sizeof v);
+    }
+    return (int64_t)NWORK * IMG_FLOATS;
+}
+
+extern "C" int32_t wrnn_wide_pack_host(const wrnn_config *cfg, const wrnn_weights *w, float *out, int64_t out_floats)
+{
+    if (!cfg || !w || !out) return fail(WRNN_ERR_INVALID, "null argument");
+    const int64_t want = wrnn_wide_packed_floats(cfg, nullptr);
+    if (want < 0) return fail(WRNN_ERR_INVALID, "the wide kernel serves fp32 RAW-512 and MOL models only");
+    if (out_floats != want) return fail(WRNN_ERR_INVALID, "out_floats must be %lld", (long long)want);
+    std::vector<float> img;
+    pack_wide(cfg->n_classes, w, img);
+    memcpy(out, img.data(), img.size() * sizeof(float));
+    return WRNN_OK;
+}
+
 extern "C" int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w)
 {
     if (!h || !w) return fail(WRNN_ERR_INVALID, "null argument");
     const float *const *pp = reinterpret_cast<const float *const *>(w);
     for (int i = 0; i < 16; ++i)
         if (!pp[i]) return fail(WRNN_ERR_INVALID, "weight pointer %d is null", i);
-    CUDA_TRY(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     if (h->dense) {
         DensePack dp;
         int32_t rc = pack_dense(h->cfg.n_classes, w, dp);
@@ -668,11 +847,49 @@ extern "C" int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w)
     pack_images(h->cfg.n_classes, h->rows5, w, img32);
     finish_images(h->rows5, h->bf16w, img32, img);
     CUDA_TRY(cudaMemcpy(h->wimg, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (h->wide) {
+        std::vector<float> wimg;
+        pack_wide(h->cfg.n_classes, w, wimg);
+        CUDA_TRY(cudaMemcpy(h->wide_img, wimg.data(), wimg.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     h->loaded = true;
     return WRNN_OK;
 }
 
 // ---- step loop launch --------------------------------------------------------------------------
+// A generate call is ENQUEUED: begin_call / end_call bracket its launches with two events and a D2H of the kernels' status
+// word into pinned memory; finish_pending (wrnn_synchronize, wrnn_get_info, the next generate call, wrnn_destroy) waits for
+// it and turns a fired watchdog into WRNN_ERR_TIMEOUT.
+static int32_t finish_pending(wrnn_handle *h)
+{
+    if (!h->pending) return WRNN_OK;
+    h->pending = false;
+    CUDA_TRY(cudaEventSynchronize(h->ev1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    h->last_status = h->status_host[0];
+    if (h->last_status != 0)
+        return fail(WRNN_ERR_TIMEOUT, "step-loop kernel watchdog fired (status %d): an exchange or pipeline barrier never completed", h->last_status);
+    return WRNN_OK;
+}
+static int32_t begin_call(wrnn_handle *h, cudaStream_t st)
+{
+    int32_t rc = finish_pending(h);          // a handle is not re-entrant: one call in flight
+    if (rc) return rc;
+    *h->progress_host = 0;
+    CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
+    CUDA_TRY(cudaEventRecord(h->ev0, st));
+    return WRNN_OK;
+}
+static int32_t end_call(wrnn_handle *h, cudaStream_t st)
+{
+    CUDA_TRY(cudaMemcpyAsync(h->status_host, h->status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaEventRecord(h->ev1, st));
+    h->pending = true;
+    return WRNN_OK;
+}
+
 // Teams per CTA and conditioning buffers per team: as many teams as there are groups (at most MAXT)
 // and double-buffered staging when it fits the opt-in shared memory, else fewer.
 static void choose_teams(const wrnn_handle *h, int G, int &T, int &nbuf)
@@ -701,24 +918,13 @@ static int32_t launch_chunk(wrnn_handle *h, KParams &p, cudaStream_t st, bool pr
     }
     h->smem_bytes = smem_map(h->rows5, h->cfg.mode, h->cfg.n_classes, p.T, p.nbuf, h->bf16w).total * (int)sizeof(float);
     h->last_teams = p.T;
+    h->last_kernel = 0;
     // epochs restart at 1 every launch: clear stale {value, epoch} pairs of the previous one
     CUDA_TRY(cudaMemsetAsync(h->xb, 0, (size_t)MAXG * xb_group(h->cpad) * sizeof(unsigned long long), st));
-    CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
-    CUDA_TRY(cudaEventRecord(h->ev0, st));
     const void *fn = probe ? (const void *)wavernn_exchange_probe_kernel
                            : persistent_kernel(p.T, model_of(h->cfg), h->bf16w, p.prof != nullptr);
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn,
-                                         dim3(NCTA), dim3(NTHREADS), args, (size_t)h->smem_bytes, st));
-    CUDA_TRY(cudaEventRecord(h->ev1, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    float ms = 0.f;
-    CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    h->last_ms += ms;
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(NCTA), dim3(NTHREADS), args, (size_t)h->smem_bytes, st));
     h->launches += 1;
-    int status[4];
-    CUDA_TRY(cudaMemcpy(status, h->status, sizeof status, cudaMemcpyDeviceToHost));
-    h->last_status = status[0];
-    if (status[0] != 0) return fail(WRNN_ERR_TIMEOUT, "persistent kernel watchdog fired (status %d): a grid-level exchange never completed", status[0]);
     return WRNN_OK;
 }
 
@@ -736,6 +942,39 @@ static void fill_common(wrnn_handle *h, KParams &p)
     p.bf16w = h->bf16w;
     p.feat = h->cfg.feat_dims;
     p.auxw = 4 * h->cfg.aux_dims;
+}
+
+// wide kernel (csrc/wavernn_wide.cuh): one cooperative launch of 128 workers + sampler CTAs per <= 21 folds
+static int32_t launch_wide(wrnn_handle *h, wrnn_wide::WParams &p, cudaStream_t st, bool probe)
+{
+    using namespace wrnn_wide;
+    p.wimg = h->wide_img;
+    p.xb = h->wide_xb;
+    p.status = h->status;
+    p.C = h->cfg.n_classes;
+    p.mode = h->cfg.mode;
+    p.n_u = h->n_u;
+    p.feat = h->cfg.feat_dims;
+    p.auxw = 4 * h->cfg.aux_dims;
+    p.nq = (p.F + 2) / 3;
+    p.nsamp = h->wide_nsamp;
+    CUDA_TRY(cudaMemsetAsync(h->wide_xb, 0, (size_t)XW_TOTAL * sizeof(unsigned), st));
+    const bool mol = h->cfg.mode == WRNN_MODE_MOL;
+    const void *fn = probe ? (const void *)wavernn_wide_probe_kernel
+                   : p.prof ? (mol ? (const void *)wavernn_wide_kernel_mol_prof : (const void *)wavernn_wide_kernel_prof)
+                            : (mol ? (const void *)wavernn_wide_kernel_mol : (const void *)wavernn_wide_kernel);
+    void *args[] = {&p};
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(NWORK + h->wide_nsamp), dim3(NTHREADS), args, (size_t)SM_BYTES, st));
+    h->smem_bytes = SM_BYTES;
+    h->last_kernel = 1;
+    h->launches += 1;
+    return WRNN_OK;
+}
+static bool use_wide(const wrnn_handle *h)
+{
+    if (!h->wide) return false;
+    const char *k = getenv("WRNN_KERNEL");                       // development knob: "grouped" forces the round-1 kernel
+    return !(k && strcmp(k, "grouped") == 0);
 }
 
 // dense step loop (csrc/wavernn_dense.cuh): one launch holds every fold; clusters are independent
@@ -765,27 +1004,25 @@ static int32_t launch_dense(wrnn_handle *h, wrnn_dense::DParams dp, bool frames,
         dp.prof = nullptr;
         dp.mol = h->cfg.mode == WRNN_MODE_MOL ? 1 : 0;
         if (h->profiling && !frames) {
-            if (!h->dense_prof) CUDA_TRY(cudaMalloc(&h->dense_prof, (size_t)h->dense_clusters * CL * PROF_N * sizeof(long long)));
-            CUDA_TRY(cudaMemsetAsync(h->dense_prof, 0, (size_t)h->dense_clusters * CL * PROF_N * sizeof(long long), st));
+            // the counters are per CTA of the launch (the grid can exceed one wave of clusters)
+            const size_t need = (size_t)ncl * CL * PROF_N;
+            if (need > h->dense_prof_slots) {
+                cudaFree(h->dense_prof);
+                h->dense_prof = nullptr;
+                h->dense_prof_slots = 0;
+                CUDA_TRY(cudaMalloc(&h->dense_prof, need * sizeof(long long)));
+                h->dense_prof_slots = need;
+            }
+            CUDA_TRY(cudaMemsetAsync(h->dense_prof, 0, h->dense_prof_slots * sizeof(long long), st));
             dp.prof = h->dense_prof;
         }
-        CUDA_TRY(cudaMemsetAsync(h->status, 0, 4 * sizeof(int), st));
-        CUDA_TRY(cudaEventRecord(h->ev0, st));
         if (frames) wavernn_dense_kernel_frames<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
         else if (dp.prof) wavernn_dense_kernel_prof<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
         else wavernn_dense_kernel<<<dim3(ncl * CL), dim3(DTHREADS), SM_TOTAL, st>>>(dp);
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaEventRecord(h->ev1, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        float ms = 0.f;
-        CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-        h->last_ms += ms;
         h->launches += 1;
         h->smem_bytes = SM_TOTAL;
-        int status[4];
-        CUDA_TRY(cudaMemcpy(status, h->status, sizeof status, cudaMemcpyDeviceToHost));
-        h->last_status = status[0];
-        if (status[0] != 0) return fail(WRNN_ERR_TIMEOUT, "dense kernel watchdog fired (wait code %d): a pipeline barrier never completed", status[0]);
+        h->last_kernel = 2;
     }
     return WRNN_OK;
 }
@@ -807,17 +1044,19 @@ extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const 
             return fail(WRNN_ERR_INVALID, "fold %d: start %lld / limit %lld outside [0, %lld]", b, (long long)fold_start[b], (long long)fold_limit[b], (long long)cond_rows);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
+    int32_t rc = begin_call(h, st);
+    if (rc) return rc;
     if (num_folds > h->fold_cap) {
         cudaFree(h->fold_dev);
         h->fold_dev = nullptr;
+        h->fold_cap = 0;
         CUDA_TRY(cudaMalloc(&h->fold_dev, (size_t)2 * num_folds * sizeof(long long)));
         h->fold_cap = num_folds;
     }
     CUDA_TRY(cudaMemcpyAsync(h->fold_dev, fold_start, (size_t)num_folds * sizeof(long long), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(h->fold_dev + h->fold_cap, fold_limit, (size_t)num_folds * sizeof(long long), cudaMemcpyHostToDevice, st));
 
-    h->last_ms = 0.f;
     if (h->dense) {
         if (cond_rows > 0x7fffffffll) return fail(WRNN_ERR_INVALID, "dense path indexes conditioning rows with 32 bits (got %lld rows)", (long long)cond_rows);
         wrnn_dense::DParams dp;
@@ -832,7 +1071,39 @@ extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const 
         dp.samples_out = samples_out;
         dp.labels_out = labels_out;
         dp.seed = seed;
-        return launch_dense(h, dp, false, num_folds, steps, st);
+        rc = launch_dense(h, dp, false, num_folds, steps, st);
+        if (rc) return rc;
+        return end_call(h, st);
+    }
+    if (use_wide(h)) {
+        // balanced launches of at most FMAX folds; a fold's arithmetic does not depend on its launch mates
+        const int nl = (num_folds + wrnn_wide::FMAX - 1) / wrnn_wide::FMAX;
+        int next = 0;
+        for (int l = 0; l < nl; ++l) {
+            const int nf = num_folds / nl + (l < num_folds % nl ? 1 : 0);
+            wrnn_wide::WParams p;
+            memset(&p, 0, sizeof p);
+            p.mels = mels;
+            p.aux = aux;
+            p.fold_start = h->fold_dev;
+            p.fold_limit = h->fold_dev + h->fold_cap;
+            p.uniforms = uniforms;
+            p.forced_x = forced_x;
+            p.logits_out = logits_out;
+            p.samples_out = samples_out;
+            p.labels_out = labels_out;
+            p.seed = seed;
+            p.prof = h->profiling ? h->prof_dev : nullptr;
+            p.progress = nl == 1 ? h->progress_dev : nullptr;
+            p.B = num_folds;
+            p.S = steps;
+            p.F = nf;
+            p.fold0 = next;
+            next += nf;
+            rc = launch_wide(h, p, st, false);
+            if (rc) return rc;
+        }
+        return end_call(h, st);
     }
     const int max_chunk = MAXG * BT;
     for (int b0 = 0; b0 < num_folds; b0 += max_chunk) {
@@ -860,10 +1131,10 @@ extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const 
             p.group_nf[g] = nf;
             next += nf;
         }
-        int32_t rc = launch_chunk(h, p, st, false);
+        rc = launch_chunk(h, p, st, false);
         if (rc) return rc;
     }
-    return WRNN_OK;
+    return end_call(h, st);
 }
 
 extern "C" int32_t wrnn_generate_folds_frames(wrnn_handle *h, const float *mel_frames, int64_t frame_rows, const float *aux_frames, int64_t aux_rows,
@@ -886,15 +1157,17 @@ extern "C" int32_t wrnn_generate_folds_frames(wrnn_handle *h, const float *mel_f
                         (long long)frame_rows, (long long)aux_rows);
     }
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
+    int32_t rc = begin_call(h, st);
+    if (rc) return rc;
     if (num_folds > h->fold_cap) {
         cudaFree(h->fold_dev);
         h->fold_dev = nullptr;
+        h->fold_cap = 0;
         CUDA_TRY(cudaMalloc(&h->fold_dev, (size_t)2 * num_folds * sizeof(long long)));
         h->fold_cap = num_folds;
     }
     CUDA_TRY(cudaMemcpyAsync(h->fold_dev, fold_geo, (size_t)num_folds * 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    h->last_ms = 0.f;
     wrnn_dense::DParams dp;
     memset(&dp, 0, sizeof dp);
     dp.mel_frames = mel_frames;
@@ -909,23 +1182,58 @@ extern "C" int32_t wrnn_generate_folds_frames(wrnn_handle *h, const float *mel_f
     dp.samples_out = samples_out;
     dp.labels_out = labels_out;
     dp.seed = seed;
-    return launch_dense(h, dp, true, num_folds, steps, st);
+    rc = launch_dense(h, dp, true, num_folds, steps, st);
+    if (rc) return rc;
+    return end_call(h, st);
+}
+
+extern "C" int32_t wrnn_synchronize(wrnn_handle *h)
+{
+    if (!h) return fail(WRNN_ERR_INVALID, "null handle");
+    DeviceGuard guard_(h->device);
+    return finish_pending(h);
+}
+
+extern "C" int32_t wrnn_query(wrnn_handle *h, int32_t *done, int32_t *steps_done)
+{
+    if (!h || !done) return fail(WRNN_ERR_INVALID, "null argument");
+    DeviceGuard guard_(h->device);
+    *done = 1;
+    if (h->pending) {
+        const cudaError_t e = cudaEventQuery(h->ev1);
+        if (e == cudaErrorNotReady) *done = 0;
+        else if (e != cudaSuccess) return fail(WRNN_ERR_CUDA, "cudaEventQuery: %s", cudaGetErrorString(e));
+    }
+    if (steps_done) *steps_done = *reinterpret_cast<volatile int *>(h->progress_host);
+    return WRNN_OK;
 }
 
 extern "C" int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *usec_per_exchange)
 {
     if (!h || !usec_per_exchange || iters <= 0) return fail(WRNN_ERR_INVALID, "bad argument");
-    CUDA_TRY(cudaSetDevice(h->device));
-    KParams p;
-    fill_common(h, p);
-    p.G = 1;
-    p.probe_iters = iters;
-    h->last_ms = 0.f;
-    int32_t rc = launch_chunk(h, p, nullptr, true);   // warm-up
-    if (rc) return rc;
-    h->last_ms = 0.f;
-    rc = launch_chunk(h, p, nullptr, true);
-    if (rc) return rc;
+    DeviceGuard guard_(h->device);
+    for (int rep = 0; rep < 2; ++rep) {          // warm-up, then the measured launch
+        int32_t rc = begin_call(h, nullptr);
+        if (rc) return rc;
+        if (use_wide(h)) {
+            wrnn_wide::WParams p;
+            memset(&p, 0, sizeof p);
+            p.F = wrnn_wide::FMAX;
+            p.probe_iters = iters;
+            rc = launch_wide(h, p, nullptr, true);
+        } else {
+            KParams p;
+            fill_common(h, p);
+            p.G = 1;
+            p.probe_iters = iters;
+            rc = launch_chunk(h, p, nullptr, true);
+        }
+        if (rc) return rc;
+        rc = end_call(h, nullptr);
+        if (rc) return rc;
+        rc = finish_pending(h);
+        if (rc) return rc;
+    }
     *usec_per_exchange = h->last_ms * 1000.f / (float)iters;
     return WRNN_OK;
 }
@@ -933,7 +1241,7 @@ extern "C" int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *u
 extern "C" int32_t wrnn_set_profiling(wrnn_handle *h, int32_t enable)
 {
     if (!h) return fail(WRNN_ERR_INVALID, "null handle");
-    CUDA_TRY(cudaSetDevice(h->device));
+    DeviceGuard guard_(h->device);
     if (h->dense) {
         h->profiling = enable != 0;
         return WRNN_OK;
@@ -946,16 +1254,17 @@ extern "C" int32_t wrnn_set_profiling(wrnn_handle *h, int32_t enable)
 extern "C" int32_t wrnn_get_stage_cycles(wrnn_handle *h, int64_t *out, int32_t n)
 {
     if (!h || !out) return fail(WRNN_ERR_INVALID, "null argument");
-    if (h->dense) {     // dense kernel: [CTAs of the last launch capacity][32] counters, slot map in csrc/wavernn_dense.cuh
+    DeviceGuard guard_(h->device);
+    int32_t rc = finish_pending(h);
+    if (rc) return rc;
+    if (h->dense) {     // dense kernel: [CTAs of the last launch][32] counters, slot map in csrc/wavernn_dense.cuh
         if (!h->dense_prof) return fail(WRNN_ERR_STATE, "profiling was never enabled");
-        const int have = h->dense_clusters * wrnn_dense::CL * wrnn_dense::PROF_N;
-        CUDA_TRY(cudaSetDevice(h->device));
-        CUDA_TRY(cudaMemcpy(out, h->dense_prof, (size_t)(n < have ? n : have) * sizeof(long long), cudaMemcpyDeviceToHost));
+        const size_t have = h->dense_prof_slots;
+        CUDA_TRY(cudaMemcpy(out, h->dense_prof, ((size_t)n < have ? (size_t)n : have) * sizeof(long long), cudaMemcpyDeviceToHost));
         return WRNN_OK;
     }
     if (!h->prof_dev) return fail(WRNN_ERR_STATE, "profiling was never enabled");
     if (n != NCTA * PROF_SLOTS) return fail(WRNN_ERR_INVALID, "n must be %d", NCTA * PROF_SLOTS);
-    CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaMemcpy(out, h->prof_dev, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost));
     return WRNN_OK;
 }
@@ -963,17 +1272,21 @@ extern "C" int32_t wrnn_get_stage_cycles(wrnn_handle *h, int64_t *out, int32_t n
 extern "C" int32_t wrnn_get_info(wrnn_handle *h, wrnn_info *out)
 {
     if (!h || !out) return fail(WRNN_ERR_INVALID, "null argument");
-    out->ctas = h->dense ? h->dense_clusters * wrnn_dense::CL : NCTA;
+    DeviceGuard guard_(h->device);
+    finish_pending(h);                           // status and time of the last call (a fired watchdog shows in last_kernel_status)
+    const bool wide = !h->dense && use_wide(h);
+    out->ctas = h->dense ? h->dense_clusters * wrnn_dense::CL : wide ? wrnn_wide::NWORK + h->wide_nsamp : NCTA;
     out->threads = h->dense ? wrnn_dense::DTHREADS : NTHREADS;
-    out->smem_bytes = h->dense ? wrnn_dense::SM_TOTAL : h->smem_bytes;
-    out->folds_per_group = h->dense ? wrnn_dense::BC : BT;
-    out->max_folds_per_launch = h->dense ? h->dense_clusters * wrnn_dense::BC : MAXG * BT;
-    out->exchanges_per_step = h->dense ? 6 : NEXCH;
+    out->smem_bytes = h->dense ? wrnn_dense::SM_TOTAL : wide ? wrnn_wide::SM_BYTES : h->smem_bytes;
+    out->folds_per_group = h->dense ? wrnn_dense::BC : wide ? wrnn_wide::FMAX : BT;
+    out->max_folds_per_launch = h->dense ? h->dense_clusters * wrnn_dense::BC : wide ? wrnn_wide::FMAX : MAXG * BT;
+    out->exchanges_per_step = h->dense ? 6 : wide ? 6 : NEXCH;
     out->sm_count = h->sm_count;
     out->launches = h->launches;
     out->epilogue_launches = g_epilogue_launches;
     out->last_kernel_status = h->last_status;
     out->last_kernel_ms = h->last_ms;
+    out->kernel_kind = h->last_kernel;
     return WRNN_OK;
 }
 
@@ -1080,7 +1393,9 @@ static int32_t xfade_impl(const float *samples, int32_t num_folds, int32_t steps
         if (t_tables_dev) cudaFree(t_tables_dev);
         t_tables_dev = nullptr;
         CUDA_TRY(cudaMalloc(&t_tables_dev, tab.size() * sizeof(double)));
-        CUDA_TRY(cudaMemcpy(t_tables_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+        // on the caller's stream (a non-blocking stream is not ordered after the legacy stream), host buffer alive until done
+        CUDA_TRY(cudaMemcpyAsync(t_tables_dev, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
         t_overlap = overlap;
         t_tail = tail_fade;
         t_device = dev;

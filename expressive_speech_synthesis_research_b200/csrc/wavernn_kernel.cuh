@@ -995,6 +995,7 @@ __device__ __forceinline__ void persistent_body(const KParams &prm)
         for (int i = 0; i < PROF_SLOTS; ++i) p.prof[(size_t)c.cta * PROF_SLOTS + i] = reinterpret_cast<long long *>(sm + c.m.prof)[i];
 }
 
+#ifndef WRNN_HELPERS_ONLY   /* development: a translation unit that only wants the device helpers above */
 #define WRNN_KERNEL(name, PROF, BF16W, TEAMS, MODEL) \
     extern "C" __global__ void __launch_bounds__(NTHREADS, 1) name(const KParams prm) { persistent_body<PROF, BF16W, TEAMS, MODEL>(prm); }
 #define WRNN_KERNELS3(stem, PROF, BF16W, MODEL) \
@@ -1050,5 +1051,6 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wavernn_exchange_probe
     }
     if (acc == 123.456f) prm.status[1] = 1;      // keep the loads alive
 }
+#endif  // WRNN_HELPERS_ONLY
 
 }  // namespace wrnn

@@ -117,6 +117,16 @@ class _Engine:
         _lib.check(self.lib.wrnn_get_info(self.handle, ctypes.byref(out)))
         return out
 
+    def synchronize(self):
+        """Wait for the generate call enqueued last; raises when an in-kernel watchdog fired (WRNN_ERR_TIMEOUT)."""
+        _lib.check(self.lib.wrnn_synchronize(self.handle))
+
+    def query(self):
+        """(done, steps_done) of the call in flight, without blocking (the gen_display hook, fatchord_version.py:220)."""
+        done, steps = _lib.i32(), _lib.i32()
+        _lib.check(self.lib.wrnn_query(self.handle, ctypes.byref(done), ctypes.byref(steps)))
+        return bool(done.value), int(steps.value)
+
     def stage_cycles(self, enable=None):
         """enable=True/False toggles in-kernel stage timing; None returns the last launch's counters
         as an int64 array [128, 32]."""
@@ -284,7 +294,7 @@ class WaveRNN(nn.Module):
                 torch.backends.cuda.matmul.allow_tf32 = prev
         return m[0].t().contiguous(), aux[0].t().contiguous()
 
-    def _run_folds_frames(self, eng, device, mel_frames, aux_frames, geo, S, uniforms, seed, forced_x, return_logits):
+    def _run_folds_frames(self, eng, device, mel_frames, aux_frames, geo, S, uniforms, seed, forced_x, return_logits, wait=True):
         """wrnn_generate_folds_frames: geo is a host int32 [B, 4] array (sample0, utterance samples, mel frame row, aux frame row)."""
         geo = np.ascontiguousarray(geo, dtype=np.int32)
         B = geo.shape[0]
@@ -312,7 +322,9 @@ class WaveRNN(nn.Module):
             eng.handle, ptr(mel_frames), mel_frames.size(0), ptr(aux_frames), aux_frames.size(0), ptr(table),
             self.hop_length, self.pad, geo.ctypes.data_as(ctypes.c_void_p), B, S,
             ptr(u), ctypes.c_uint64(seed), ptr(fx), ptr(logits), ptr(samples), ptr(labels), ctypes.c_void_p(stream)))
-        return dict(samples=samples, labels=labels, logits=logits)
+        if wait:
+            eng.synchronize()
+        return dict(samples=samples, labels=labels, logits=logits, keep=(u, fx, geo))
 
     # ------------------------------------------------------------------ the hot path
     def generate(self, mels, *args, uniforms=None, seed=None, forced_x=None, return_logits=False,
@@ -397,19 +409,20 @@ class WaveRNN(nn.Module):
             starts = np.zeros(1, dtype=np.int64)
         if frames:
             geo = np.stack([starts, np.full(B, L), np.zeros(B), np.zeros(B)], axis=1)
-            res = self._run_folds_frames(eng, device, mel_fr, aux_fr, geo, S, uniforms, seed, forced_x, return_logits)
+            res = self._run_folds_frames(eng, device, mel_fr, aux_fr, geo, S, uniforms, seed, forced_x, return_logits, wait=False)
         else:
             limits = np.full(B, L, dtype=np.int64)
-            res = self._run_folds(eng, device, m_up, aux, starts, limits, S, uniforms, seed, forced_x, return_logits)
+            res = self._run_folds(eng, device, m_up, aux, starts, limits, S, uniforms, seed, forced_x, return_logits, wait=False)
         wav = torch.empty(wave_len, dtype=torch.float64, device=device)
         stream = torch.cuda.current_stream(device).cuda_stream
         _lib.check(eng.lib.wrnn_xfade_unfold(res["samples"].data_ptr(), B, S, int(batched), overlap if batched else 0,
                                              self.n_classes if mu_law else 0, wave_len, tail, wav.data_ptr(),
                                              ctypes.c_void_p(stream)))
+        eng.synchronize()                                             # step loop + epilogue were enqueued; a fired watchdog raises here
         self.last_stats.update(folds=B, steps=S, wave_len=wave_len, kernel_ms=eng.info().last_kernel_ms)
         return wav, res
 
-    def _run_folds(self, eng, device, m_up, aux, starts, limits, S, uniforms, seed, forced_x, return_logits):
+    def _run_folds(self, eng, device, m_up, aux, starts, limits, S, uniforms, seed, forced_x, return_logits, wait=True):
         """wrnn_generate_folds over conditioning rows; starts/limits are host int64 arrays."""
         B = len(starts)
         n_u = 1 if self.mode == 'RAW' else self.n_classes // 3 + 1
@@ -438,7 +451,9 @@ class WaveRNN(nn.Module):
             starts.ctypes.data_as(ctypes.c_void_p), limits.ctypes.data_as(ctypes.c_void_p), B, S,
             ptr(u), ctypes.c_uint64(seed), ptr(fx), ptr(logits), ptr(samples), ptr(labels),
             ctypes.c_void_p(stream)))
-        return dict(samples=samples, labels=labels, logits=logits)
+        if wait:
+            eng.synchronize()
+        return dict(samples=samples, labels=labels, logits=logits, keep=(u, fx))      # keep: inputs of the enqueued call stay alive
 
     def generate_many(self, mel_list, target, overlap, mu_law, uniforms=None, seed=None):
         """Batched generation of several utterances with their folds POOLED into one launch
@@ -508,7 +523,7 @@ class WaveRNN(nn.Module):
                                 mb += mf.size(0)
                                 ab += af.size(0)
                             m_all, a_all = torch.cat(mfs), torch.cat(afs)
-                            res = self._run_folds_frames(eng, device, m_all, a_all, np.concatenate(geo), S, u, sd, None, False)
+                            res = self._run_folds_frames(eng, device, m_all, a_all, np.concatenate(geo), S, u, sd, None, False, wait=False)
                         else:
                             rows = sum(plan[i][1] for i in chunk)
                             m_all = torch.empty(rows, self._feat_dims, dtype=torch.float32, device=device)
@@ -525,8 +540,7 @@ class WaveRNN(nn.Module):
                                 starts.append(base + np.arange(B, dtype=np.int64) * (target + overlap))
                                 limits.append(np.full(B, base + L, dtype=np.int64))
                                 base += L
-                            res = self._run_folds(eng, device, m_all, a_all, np.concatenate(starts), np.concatenate(limits), S, u, sd, None, False)
-                        kernel_ms += eng.info().last_kernel_ms
+                            res = self._run_folds(eng, device, m_all, a_all, np.concatenate(starts), np.concatenate(limits), S, u, sd, None, False, wait=False)
                         b0 = 0
                         for i in chunk:
                             B, _, wave_len = plan[i]
@@ -537,7 +551,9 @@ class WaveRNN(nn.Module):
                             outs[i] = wav
                             b0 += B
                         fold0 += nf
-                        torch.cuda.current_stream(device).synchronize()     # the chunk's buffers are reused by the next one
+                        eng.synchronize()                                    # the chunk's buffers are reused by the next one
+                        torch.cuda.current_stream(device).synchronize()
+                        kernel_ms += eng.info().last_kernel_ms
                         del m_all, a_all, res
                     b0 = total_folds
                     self.last_stats.update(folds=b0, steps=S, kernel_ms=kernel_ms, chunks=len(chunks))

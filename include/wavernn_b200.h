@@ -11,8 +11,12 @@
  * returns 0 on success or a negative wrnn_status; wrnn_last_error() gives the thread-local
  * message.  Pointers marked [dev] are CUDA device pointers borrowed for the duration of the
  * call; [host] are host pointers.  `stream` is a cudaStream_t passed as void* (NULL = default
- * stream).  Work is enqueued asynchronously on `stream` unless stated otherwise.  One handle
- * per device; a handle is NOT re-entrant (the persistent kernel occupies 128 SMs).
+ * stream).  The generate and epilogue entry points ENQUEUE their work on `stream` and return; a
+ * fired in-kernel watchdog is reported by wrnn_synchronize / the next generate call on the
+ * handle (WRNN_ERR_TIMEOUT).  wrnn_load_weights and wrnn_measure_exchange are synchronous.
+ * One handle per device; a handle is NOT re-entrant: one generate call in flight (the
+ * persistent kernels occupy every SM), a second one first waits for the first.
+ * Entry points leave the caller's current CUDA device unchanged.
  * There is no CPU fallback: every compute entry point fails with WRNN_ERR_CUDA when no
  * sm_100 device is usable.
  */
@@ -25,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WRNN_ABI_VERSION 1
+#define WRNN_ABI_VERSION 2
 
 typedef enum {
     WRNN_OK = 0,
@@ -88,6 +92,14 @@ int32_t wrnn_load_weights(wrnn_handle *h, const wrnn_weights *w /* [host] */);
 int64_t wrnn_packed_floats(const wrnn_config *cfg);
 int32_t wrnn_pack_weights_host(const wrnn_config *cfg, const wrnn_weights *w /* [host] */,
                                float *out /* [host] */, int64_t out_floats);
+
+/* The same for the WIDE kernel (csrc/wavernn_wide.cuh: every fold of a launch, up to 21, through one exchange per stage;
+ * fp32, RAW with 512 classes or MOL): [128 worker CTAs][wrnn_wide_packed_floats / 128] floats; layout[8] = {floats per
+ * CTA, offsets of Wih2x, Whh1, Whh2 (gate layout), fc1, fc2, fc3 (fc layout), the conditioning block}; the small vectors
+ * follow the conditioning block.  Returns -1 / WRNN_ERR_INVALID for configurations the wide kernel does not serve. */
+int64_t wrnn_wide_packed_floats(const wrnn_config *cfg, int64_t *layout /* [host] int64[8] or NULL */);
+int32_t wrnn_wide_pack_host(const wrnn_config *cfg, const wrnn_weights *w /* [host] */,
+                            float *out /* [host] */, int64_t out_floats);
 
 /* Host-only view of the WRNN_PREC_BF16_DENSE repack (no GPU needed), used by the CPU tests to replay the kernel's
  * tensor-core program in numpy.  layout[8] = {bundles per step, stream bytes per CTA rank, sizeof(bundle record),
@@ -179,6 +191,15 @@ int32_t wrnn_xfade_unfold_segment(const float *samples, int32_t num_rows, int32_
                                   int64_t first_fold, int64_t total_folds, int64_t seg_start, int64_t seg_len,
                                   double *out, void *stream);
 
+/* Wait for the generate call enqueued last on this handle (if any) and report its outcome: WRNN_ERR_TIMEOUT when an
+ * in-kernel watchdog fired.  wrnn_get_info also waits (it reports the call's device time and status). */
+int32_t wrnn_synchronize(wrnn_handle *h);
+
+/* Non-blocking progress of the call in flight: *done = 1 when nothing is pending; *steps_done = sample steps completed so far
+ * (written by the step loop every 128 steps into mapped host memory; single-launch calls of the wide kernel only, else 0).
+ * Replaces the reference's gen_display progress line, fatchord_version.py:220,246-250. */
+int32_t wrnn_query(wrnn_handle *h, int32_t *done, int32_t *steps_done /* may be NULL */);
+
 /* Introspection used by bench.py / tests. */
 typedef struct {
     int32_t ctas;                /* CTAs of the persistent kernel (one per SM) */
@@ -192,6 +213,7 @@ typedef struct {
     int64_t epilogue_launches;
     int32_t last_kernel_status;  /* 0 ok, else WRNN_ERR_TIMEOUT */
     float   last_kernel_ms;      /* device time of the last generate_folds (CUDA events) */
+    int32_t kernel_kind;         /* step-loop kernel of the last launch: 0 grouped FFMA (round 1), 1 wide FFMA, 2 dense tcgen05 */
 } wrnn_info;
 int32_t wrnn_get_info(wrnn_handle *h, wrnn_info *out);
 
@@ -202,9 +224,9 @@ int32_t wrnn_get_info(wrnn_handle *h, wrnn_info *out);
 int32_t wrnn_set_profiling(wrnn_handle *h, int32_t enable);
 int32_t wrnn_get_stage_cycles(wrnn_handle *h, int64_t *out /* [host] */, int32_t n);
 
-/* Microbenchmark of the grid-level exchange used by the step loop (each CTA publishes 32
- * {value, epoch} pairs, then polls / gathers the 4096 pairs of the whole vector from L2),
- * `iters` times on an otherwise empty persistent kernel.
+/* Microbenchmark of the grid-level exchange used by the step loop (wide kernel: each worker CTA publishes its 4 units
+ * x 7 quads {3 values, epoch}, every warp then polls the 224 quads of its 32 units from L2 -- 56 KB per CTA; grouped
+ * kernel: 32 {value, epoch} pairs published, 4096 gathered), `iters` times on an otherwise empty persistent kernel.
  * Writes the mean device time per exchange in microseconds.  Synchronous. */
 int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *usec_per_exchange);
 

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_header_symbols():
     L = ctypes.CDLL(path)
     for name in declared:
         assert hasattr(L, name), name
-    assert _lib.lib().wrnn_abi_version() == 1
+    assert _lib.lib().wrnn_abi_version() == _lib.ABI_VERSION
 
 
 def test_fold_index_matches_oracle_grid():
