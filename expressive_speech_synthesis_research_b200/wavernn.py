@@ -324,7 +324,7 @@ class WaveRNN(nn.Module):
             ptr(u), ctypes.c_uint64(seed), ptr(fx), ptr(logits), ptr(samples), ptr(labels), ctypes.c_void_p(stream)))
         if wait:
             eng.synchronize()
-        return dict(samples=samples, labels=labels, logits=logits, keep=(u, fx, geo))
+        return dict(samples=samples, labels=labels, logits=logits)
 
     # ------------------------------------------------------------------ the hot path
     def generate(self, mels, *args, uniforms=None, seed=None, forced_x=None, return_logits=False,
@@ -453,7 +453,7 @@ class WaveRNN(nn.Module):
             ctypes.c_void_p(stream)))
         if wait:
             eng.synchronize()
-        return dict(samples=samples, labels=labels, logits=logits, keep=(u, fx))      # keep: inputs of the enqueued call stay alive
+        return dict(samples=samples, labels=labels, logits=logits)    # u / fx return to torch's stream-ordered allocator: safe on this stream
 
     def generate_many(self, mel_list, target, overlap, mu_law, uniforms=None, seed=None):
         """Batched generation of several utterances with their folds POOLED into one launch

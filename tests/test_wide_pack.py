@@ -1,5 +1,5 @@
 """CPU test of the WIDE kernel's host-side weight repack (wrnn_wide_pack_host, csrc/wavernn_wide.cuh): decode the packed
-per-CTA images with the index arithmetic the kernel's lanes use (pass<3>, pass<1>, cond_pass), re-run the step dataflow in
+per-CTA images with the index arithmetic the kernel's lanes use (pass_tile, pass4, cond_pass), re-run the step dataflow in
 numpy float64 and compare the teacher-forced logits with the fp64 oracle.  Pins the algebraic folding, the
 [warp][ig][ks][unit] weight layouts, the 176-wide conditioning K space and the row ownership without a GPU."""
 import ctypes
@@ -32,7 +32,7 @@ def pack(sd, mode):
 
 
 def gate_matrix(img, off):
-    """RB = 3 layout -> [cta][gate 3][unit 4][k 512], read the way pass<3> does: lane (ks, u) of warp w, block ig, element
+    """RB = 3 layout -> [cta][gate 3][unit 4][k 512], read the way pass_tile does: lane (ks, u) of warp w, block ig, element
     ii*3 + gate multiplies x[k = 32 w + 2 (4 ig + ii) + ks]."""
     blk = img[:, off:off + 12 * HID].reshape(NWORK, 16, 4, 2, 4, 4, 3).astype(np.float64)   # [cta][w][ig][ks][u][ii][g]
     out = np.zeros((NWORK, 3, 4, HID))
@@ -46,15 +46,27 @@ def gate_matrix(img, off):
 
 
 def fc_matrix(img, off):
-    """RB = 1 layout -> [cta][unit 4][k 512]: element e of block q multiplies x[k = 32 w + 2 (4 q + e) + ks]."""
-    blk = img[:, off:off + 4 * HID].reshape(NWORK, 16, 4, 2, 4, 4).astype(np.float64)       # [cta][w][q][ks][u][e]
+    """fc layout -> [cta][unit 4][k 512]: pass4's lane ks reads the four rows of k = 32 w + 4 i + ks as one float4."""
+    blk = img[:, off:off + 4 * HID].reshape(NWORK, 16, 8, 4, 4).astype(np.float64)           # [cta][w][i][ks][u]
     out = np.zeros((NWORK, 4, HID))
     for w in range(16):
-        for q in range(4):
-            for ks in range(2):
-                for e in range(4):
-                    out[:, :, 32 * w + 2 * (4 * q + e) + ks] = blk[:, w, q, ks, :, e]
+        for i in range(8):
+            for ks in range(4):
+                out[:, :, 32 * w + 4 * i + ks] = blk[:, w, i, ks, :]
     return out
+
+
+def four_row_block(img, off):
+    """4-row layout [w][i 16][ks 2][u 4][row 4] -> (gates [cta][3][4][512], fc row [cta][4][512]), k = 32 w + 2 i + ks."""
+    blk = img[:, off:off + 16 * HID].reshape(NWORK, 16, 16, 2, 4, 4).astype(np.float64)        # [cta][w][i][ks][u][row]
+    gates, fc = np.zeros((NWORK, 3, 4, HID)), np.zeros((NWORK, 4, HID))
+    for w in range(16):
+        for i in range(16):
+            for ks in range(2):
+                k = 32 * w + 2 * i + ks
+                gates[:, :, :, k] = blk[:, w, i, ks, :, :3].transpose(0, 2, 1)
+                fc[:, :, k] = blk[:, w, i, ks, :, 3]
+    return gates, fc
 
 
 def cond_matrices(img, off):
@@ -71,11 +83,12 @@ def cond_matrices(img, off):
 
 class Emu:
     def __init__(self, img, layout, C):
-        per, ih2, hh1, hh2, fc1, fc2, fc3, wc = layout
+        per, ih2, hh1, t4b, fc2, fc3, wc, _ = layout
         assert img.shape[1] == per
         self.C = C
-        self.IH2, self.HH1, self.HH2 = gate_matrix(img, ih2), gate_matrix(img, hh1), gate_matrix(img, hh2)
-        self.FC1, self.FC2, self.FC3 = fc_matrix(img, fc1), fc_matrix(img, fc2), fc_matrix(img, fc3)
+        self.IH2, self.HH1 = gate_matrix(img, ih2), gate_matrix(img, hh1)
+        self.HH2, self.FC1 = four_row_block(img, t4b)
+        self.FC2, self.FC3 = fc_matrix(img, fc2), fc_matrix(img, fc3)
         self.WC = cond_matrices(img, wc)
         self.sv = img[:, wc + KC2 * 32: wc + KC2 * 32 + 128].astype(np.float64)
 
