@@ -409,9 +409,8 @@ static void pack_images(int C, int rows5, const wrnn_weights *w, std::vector<flo
 
 // ---- wide kernel images (csrc/wavernn_wide.cuh) --------------------------------------------------
 // Same algebra as pack_images (input layer folded in fp64, rounded once to fp32); different layouts:
-//   gate matrices  [warp 16][ig 4][ks 2][unit 4][ii 4][gate 3]   k = 32 warp + 2 (4 ig + ii) + ks   (Wih2x, Whh1)
-//   4-row block    [warp 16][i 16][ks 2][unit 4][row 4]          k = 32 warp + 2 i + ks              (Whh2 gates | fc1 row)
-//   fc matrices    [warp 16][i 8][ks 4][unit 4]                  k = 32 warp + 4 i + ks
+//   gate matrices  [warp 16][ig 4][ks 2][unit 4][ii 4][gate 3]   k = 32 warp + 2 (4 ig + ii) + ks   (Wih2x, Whh1, Whh2)
+//   fc matrices    [k 512][unit 4]                                                                   (fc1, fc2, fc3)
 //   conditioning   [k' 176][row block 8][4]: row block = which * 4 + unit, rows {P1 r, z, n, P3} (which 0) or
 //                  {P2 r, z, n, P4} (which 1); k' < 112: mel + a1 columns; [112, 144): a3 (which 0: the P3 row only) or
 //                  a2 (which 1: the P2 rows only); [144, 176): a4 (which 1: the P4 row only)
@@ -453,25 +452,12 @@ static void pack_wide(int C, const wrnn_weights *w, std::vector<float> &img)
         };
         gate_matrix(OFF_IH2, w->r2_wih, R + A);
         gate_matrix(OFF_HH1, w->r1_whh, R);
-        // 4-row layout [warp][i 16][ks 2][unit 4][row 4], k = 32 warp + 2 i + ks: rows 0..2 = Whh2 gates, row 3 = fc1[:, :512]
-        for (int wp = 0; wp < 16; ++wp)
-            for (int i = 0; i < 16; ++i)
-                for (int ks = 0; ks < 2; ++ks)
-                    for (int u = 0; u < UNITS; ++u) {
-                        const int k = 32 * wp + 2 * i + ks;
-                        float *dst = base + OFF_T4B + (((wp * 16 + i) * 2 + ks) * 4 + u) * 4;
-                        for (int g = 0; g < 3; ++g) dst[g] = w->r2_whh[(size_t)(j0 + u + R * g) * R + k];
-                        dst[3] = w->fc1_w[(size_t)(j0 + u) * (R + A) + k];
-                    }
+        gate_matrix(OFF_HH2, w->r2_whh, R);
         auto fc_matrix = [&](int off, const float *M, int ld, int rows_valid) {
-            for (int wp = 0; wp < 16; ++wp)
-                for (int i = 0; i < 8; ++i)
-                    for (int ks = 0; ks < 4; ++ks)
-                        for (int u = 0; u < UNITS; ++u) {
-                            const int k = 32 * wp + 4 * i + ks, row = j0 + u;
-                            base[off + ((wp * 8 + i) * 4 + ks) * 4 + u] = row < rows_valid ? M[(size_t)row * ld + k] : 0.f;
-                        }
+            for (int k = 0; k < R; ++k)
+                for (int u = 0; u < UNITS; ++u) base[off + k * 4 + u] = j0 + u < rows_valid ? M[(size_t)(j0 + u) * ld + k] : 0.f;
         };
+        fc_matrix(OFF_FC1, w->fc1_w, R + A, R);
         fc_matrix(OFF_FC2, w->fc2_w, R + A, R);
         fc_matrix(OFF_FC3, w->fc3_w, R, C);              // class = 4 * cta + unit (MOL: 30 rows, CTAs 0..7)
         float *wc = base + OFF_WC;
@@ -805,7 +791,7 @@ extern "C" int64_t wrnn_wide_packed_floats(const wrnn_config *cfg, int64_t *layo
     if (!cfg || derive_layout(*cfg, rows5, nprod5, n_u) || !wide_supported(*cfg)) return -1;
     using namespace wrnn_wide;
     if (layout) {
-        const int64_t v[8] = {IMG_FLOATS, OFF_IH2, OFF_HH1, OFF_T4B, OFF_FC2, OFF_FC3, OFF_WC, 0};
+        const int64_t v[8] = {IMG_FLOATS, OFF_IH2, OFF_HH1, OFF_HH2, OFF_FC1, OFF_FC2, OFF_FC3, OFF_WC};
         memcpy(layout, v, sizeof v);
     }
     return (int64_t)NWORK * IMG_FLOATS;

@@ -95,7 +95,7 @@ int32_t wrnn_pack_weights_host(const wrnn_config *cfg, const wrnn_weights *w /* 
 
 /* The same for the WIDE kernel (csrc/wavernn_wide.cuh: every fold of a launch, up to 21, through one exchange per stage;
  * fp32, RAW with 512 classes or MOL): [128 worker CTAs][wrnn_wide_packed_floats / 128] floats; layout[8] = {floats per
- * CTA, offsets of Wih2x, Whh1 (gate layout), Whh2 | fc1 (4-row layout), fc2, fc3 (fc layout), the conditioning block, 0}; the small vectors
+ * CTA, offsets of Wih2x, Whh1, Whh2 (gate layout), fc1, fc2, fc3 (fc layout), the conditioning block}; the small vectors
  * follow the conditioning block.  Returns -1 / WRNN_ERR_INVALID for configurations the wide kernel does not serve. */
 int64_t wrnn_wide_packed_floats(const wrnn_config *cfg, int64_t *layout /* [host] int64[8] or NULL */);
 int32_t wrnn_wide_pack_host(const wrnn_config *cfg, const wrnn_weights *w /* [host] */,

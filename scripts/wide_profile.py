@@ -11,9 +11,9 @@ from expressive_speech_synthesis_research_b200 import WaveRNN  # noqa: E402
 from oracle import synth  # noqa: E402
 
 SLOTS = ["SA wait x (sampler hop)", "SA gru1 + publish H1", "S2 gather H1", "S2 pass Wih2x + A + store + B", "S2 sum + C + gru2 + publish H2",
-         "S2 deferred (Whh1, Wfc1x) + D + finalize", "S3 gather H2", "S3 pass Wfc1x + A + store + B", "S3 sum + C + fc1 + publish Y1",
-         "S3 deferred (Whh2) + D + finalize", "S4 gather Y1", "S4 pass Wfc2 + A + store + B", "S4 sum + fc2 + publish Y2",
-         "cond: D + finalize + E", "S5 gather Y2", "S5 pass Wfc3 + A + store + B", "S5 sum + publish logits", "cond: wait for the TMA rows", "cond: pass", "S5 finalize: sum of 16 partials", "-", "-", "-", "S5 finalize: bar96"]
+         "S2 deferred (Whh1, Wfc1x) + D + finalize", "S3 deferred: warp 0 pass (Whh2)", "S3 pass Wfc1x + A + store + B", "S3 sum + C + fc1 + publish Y1",
+         "S3 deferred: D + finalize", "S3 deferred: fold halves + store", "S4 pass Wfc2 + A + store + B", "S4 sum + fc2 + publish Y2",
+         "cond: D + finalize + E", "S3 deferred: gather finish (Y1)", "S5 pass Wfc3 + A + store + B", "S5 sum + publish logits", "cond: wait for the TMA rows", "cond: pass", "S5 finalize: sum of 16 partials", "S5 gather Y2", "-", "-", "S5 finalize: bar96"]
 
 
 def main():
@@ -38,7 +38,7 @@ def main():
             ms = info.last_kernel_ms
             print("B=%d kernel_kind=%d profiling=%s: %.3f ms, %.2f us/step" % (B, info.kernel_kind, prof, ms, ms * 1e3 / S), flush=True)
         cyc = eng.stage_cycles().astype(np.float64) / S
-        tot = cyc[:, :20].sum(1) + cyc[:, 23]
+        tot = cyc[:, :21].sum(1) + cyc[:, 23]
         print("  cycles/step: cta0 total %.0f  mean %.0f  max %.0f" % (tot[0], tot.mean(), tot.max()))
         print("  gathers (4 per step, thread 0): issue -> first answers %.0f clk each, stale poll rounds %.2f each, whole gather %.0f clk each"
               % (cyc[:, 20].mean() / 4, cyc[:, 21].mean() / 4, cyc[:, 22].mean() / 4))

@@ -46,27 +46,8 @@ def gate_matrix(img, off):
 
 
 def fc_matrix(img, off):
-    """fc layout -> [cta][unit 4][k 512]: pass4's lane ks reads the four rows of k = 32 w + 4 i + ks as one float4."""
-    blk = img[:, off:off + 4 * HID].reshape(NWORK, 16, 8, 4, 4).astype(np.float64)           # [cta][w][i][ks][u]
-    out = np.zeros((NWORK, 4, HID))
-    for w in range(16):
-        for i in range(8):
-            for ks in range(4):
-                out[:, :, 32 * w + 4 * i + ks] = blk[:, w, i, ks, :]
-    return out
-
-
-def four_row_block(img, off):
-    """4-row layout [w][i 16][ks 2][u 4][row 4] -> (gates [cta][3][4][512], fc row [cta][4][512]), k = 32 w + 2 i + ks."""
-    blk = img[:, off:off + 16 * HID].reshape(NWORK, 16, 16, 2, 4, 4).astype(np.float64)        # [cta][w][i][ks][u][row]
-    gates, fc = np.zeros((NWORK, 3, 4, HID)), np.zeros((NWORK, 4, HID))
-    for w in range(16):
-        for i in range(16):
-            for ks in range(2):
-                k = 32 * w + 2 * i + ks
-                gates[:, :, :, k] = blk[:, w, i, ks, :, :3].transpose(0, 2, 1)
-                fc[:, :, k] = blk[:, w, i, ks, :, 3]
-    return gates, fc
+    """fc layout [k 512][unit 4] -> [cta][unit 4][k 512]"""
+    return img[:, off:off + 4 * HID].reshape(NWORK, HID, 4).astype(np.float64).transpose(0, 2, 1)
 
 
 def cond_matrices(img, off):
@@ -83,12 +64,11 @@ def cond_matrices(img, off):
 
 class Emu:
     def __init__(self, img, layout, C):
-        per, ih2, hh1, t4b, fc2, fc3, wc, _ = layout
+        per, ih2, hh1, hh2, fc1, fc2, fc3, wc = layout
         assert img.shape[1] == per
         self.C = C
-        self.IH2, self.HH1 = gate_matrix(img, ih2), gate_matrix(img, hh1)
-        self.HH2, self.FC1 = four_row_block(img, t4b)
-        self.FC2, self.FC3 = fc_matrix(img, fc2), fc_matrix(img, fc3)
+        self.IH2, self.HH1, self.HH2 = gate_matrix(img, ih2), gate_matrix(img, hh1), gate_matrix(img, hh2)
+        self.FC1, self.FC2, self.FC3 = fc_matrix(img, fc1), fc_matrix(img, fc2), fc_matrix(img, fc3)
         self.WC = cond_matrices(img, wc)
         self.sv = img[:, wc + KC2 * 32: wc + KC2 * 32 + 128].astype(np.float64)
 
