@@ -107,11 +107,13 @@ def finish_sharded(local_samples, lo, hi, num_folds, target, overlap, mu_law_cla
         return span
     sizes = [max(0, segment_bounds(a, b, num_folds, target, overlap, wave_len)[1]
                  - segment_bounds(a, b, num_folds, target, overlap, wave_len)[0]) if b > a else 0 for a, b in ranges]
+    # result assembly (not part of the step path): every rank's span travels ONCE, to the root only -- the round-1 all_gather
+    # moved world x waveform bytes to every rank (106 MB x 8 for a 10-minute utterance)
     width = max(sizes + [1])
     padded = torch.zeros(width, dtype=torch.float64, device=dev)
     padded[:span.numel()] = span
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded, group=group)               # result assembly, not part of the step path
+    parts = [torch.empty_like(padded) for _ in range(world)] if rank == gather_to else None
+    dist.gather(padded, parts, dst=gather_to if group is None else dist.get_global_rank(group, gather_to), group=group)
     if rank != gather_to:
         return None
     return torch.cat([p[:n] for p, n in zip(parts, sizes)])
@@ -127,13 +129,15 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
     try:
         with torch.no_grad():
             device = model._device()
-            eng = model._engine(device)
             with torch.cuda.device(device):
+                eng = model._engine(device)
+                nfolds_total, _ = _lib.fold_index(mels.size(-1) * model.hop_length, target, overlap)
+                eng = model._pick_engine(eng, device, -(-nfolds_total // world))      # regime by the folds of ONE rank
                 mels = mels.to(device=device, dtype=torch.float32)
                 if model.upsample.resnet.conv_in.weight.device != device:
                     model.to(device)
                 wave_len = (mels.size(-1) - 1) * model.hop_length
-                frames = model._frames_mode()                 # dense kernel: conditioning expanded in the kernel, as generate() does
+                frames = model._frames_mode(eng)              # dense kernel: conditioning expanded in the kernel, as generate() does
                 if frames:
                     mel_fr, aux_fr = model.conditioning_frames(mels)
                     L = mels.size(-1) * model.hop_length

@@ -172,6 +172,27 @@ def _capture_generate(m, mel, batched, target, overlap, mu_law, U):
     return wav, samples
 
 
+def golden_losses():
+    """Training losses (train_wavernn.py:28-44): the reference's discretized_mix_logistic_loss
+    (utility/distribution.py:16-84) on random mixture parameters, reduce=True and False, including targets
+    in the edge bins and a narrow component (the cdf_delta <= 1e-5 branch)."""
+    ref_shim.install_reference()
+    from utility.distribution import discretized_mix_logistic_loss
+    g = {}
+    gen = torch.Generator().manual_seed(21)
+    B, T, K = 3, 50, 10
+    y_hat = torch.randn(B, T, 3 * K, generator=gen)
+    y_hat[..., 2 * K:] = y_hat[..., 2 * K:] * 2 - 4                  # log-scales around -4
+    y_hat[0, :5, 2 * K:] = -16.0                                     # very narrow components
+    y = torch.rand(B, T, 1, generator=gen) * 2 - 1
+    y[1, :4, 0] = torch.tensor([-1.0, -0.9995, 0.9995, 1.0])         # edge bins
+    g["mol_y_hat"], g["mol_y"] = y_hat.numpy(), y.numpy()
+    g["mol_loss"] = np.array(discretized_mix_logistic_loss(y_hat, y).item())
+    g["mol_loss_unreduced"] = discretized_mix_logistic_loss(y_hat, y, reduce=False).numpy()
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **g)
+    print("losses.npz")
+
+
 def golden_free_running():
     """End-to-end generate() (fatchord_version.py:150-243) with pre-drawn uniforms."""
     g = {}
@@ -223,5 +244,6 @@ if __name__ == "__main__":
     golden_conditioning()
     golden_teacher_forced()
     golden_free_running()
+    golden_losses()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -8,8 +8,8 @@ profile (8 addmm + 2 gru_cell + softmax/sampling per step).  It is what
 /root/reference does not exist; it also provides the conditioning-network oracle
 (`upsample`) for the product's PyTorch UpsampleNetwork.
 
-Pinned against the live reference by tests/test_oracle_vs_reference.py (container
-only) and against tests/golden/*.npz everywhere.
+Pinned against the goldens minted from the live reference (oracle/make_golden.py ->
+tests/golden/*.npz) by tests/test_oracle_golden.py.
 """
 import numpy as np
 import torch
