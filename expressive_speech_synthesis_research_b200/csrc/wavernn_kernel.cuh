@@ -623,7 +623,7 @@ __device__ __forceinline__ void sample_mol(Ctx &c, int g, int s, unsigned epoch)
     }
     __syncwarp();
     float best = -INFINITY;
-    int arg = 1 << 20;
+    int arg = cs;                   // a valid index even when every comparison fails (NaN logits)
     for (int i = cs; i < nr; i += 4) {
         const float u = (float)(1e-5 + ((1.0 - 1e-5) - 1e-5) * (double)pg[PG_U + f * 11 + i]);
         const float t = lg[i * BT + f] - logf(-logf(u));

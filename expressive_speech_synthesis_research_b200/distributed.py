@@ -159,8 +159,18 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                     local = res["samples"]
                 else:
                     local = torch.empty(0, S, dtype=torch.float32, device=device)
-                wav = finish_sharded(local, lo, hi, B, target, overlap, model.n_classes if mu_law else 0, wave_len,
-                                     20 * model.hop_length, group=group, gather_to=gather_to)
-                return None if wav is None else wav.cpu().numpy()
+                # same decode policy as WaveRNN.generate: bit-exact numpy mu-law + tail fade on the host below 2 M samples
+                host_mu = bool(mu_law) and gather_to is not None and (
+                    model.mu_law_decode == "host" or (model.mu_law_decode == "auto" and wave_len < 2_000_000))
+                wav = finish_sharded(local, lo, hi, B, target, overlap, model.n_classes if (mu_law and not host_mu) else 0, wave_len,
+                                     0 if host_mu else 20 * model.hop_length, group=group, gather_to=gather_to)
+                if wav is None:
+                    return None
+                wav = wav.cpu().numpy()
+                if host_mu:
+                    mu = model.n_classes - 1
+                    wav = np.sign(wav) / mu * ((1 + mu) ** np.abs(wav) - 1)             # decode_mu_law, dsp.py:100-105
+                    wav[-20 * model.hop_length:] *= np.linspace(1, 0, 20 * model.hop_length)   # fatchord_version.py:235-237
+                return wav
     finally:
         model.train()
