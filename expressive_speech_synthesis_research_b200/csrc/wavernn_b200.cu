@@ -964,11 +964,16 @@ static int32_t launch_wide(wrnn_handle *h, wrnn_wide::WParams &p, cudaStream_t s
     h->launches += 1;
     return WRNN_OK;
 }
-static bool use_wide(const wrnn_handle *h)
+// Which fp32 kernel serves `num_folds` folds: the wide kernel's step (15 us) hardly depends on the fold count, the grouped
+// kernel's is 11.5 us for one group of <= 8 folds and 15.7 / 24 us for two / three (profiles/r02_summary.md): wide above 8.
+// WRNN_KERNEL=grouped | wide forces one (development knob).
+static bool use_wide(const wrnn_handle *h, int num_folds)
 {
     if (!h->wide) return false;
-    const char *k = getenv("WRNN_KERNEL");                       // development knob: "grouped" forces the round-1 kernel
-    return !(k && strcmp(k, "grouped") == 0);
+    const char *k = getenv("WRNN_KERNEL");
+    if (k && strcmp(k, "grouped") == 0) return false;
+    if (k && strcmp(k, "wide") == 0) return true;
+    return num_folds > BT;
 }
 
 // dense step loop (csrc/wavernn_dense.cuh): one launch holds every fold; clusters are independent
@@ -1069,7 +1074,7 @@ extern "C" int32_t wrnn_generate_folds(wrnn_handle *h, const float *mels, const 
         if (rc) return rc;
         return end_call(h, st);
     }
-    if (use_wide(h)) {
+    if (use_wide(h, num_folds)) {
         // balanced launches of at most FMAX folds; a fold's arithmetic does not depend on its launch mates
         const int nl = (num_folds + wrnn_wide::FMAX - 1) / wrnn_wide::FMAX;
         int next = 0;
@@ -1209,7 +1214,7 @@ extern "C" int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *u
     for (int rep = 0; rep < 2; ++rep) {          // warm-up, then the measured launch
         int32_t rc = begin_call(h, nullptr);
         if (rc) return rc;
-        if (use_wide(h)) {
+        if (use_wide(h, wrnn_wide::FMAX)) {
             wrnn_wide::WParams p;
             memset(&p, 0, sizeof p);
             p.F = wrnn_wide::FMAX;
@@ -1268,7 +1273,7 @@ extern "C" int32_t wrnn_get_info(wrnn_handle *h, wrnn_info *out)
     if (!h || !out) return fail(WRNN_ERR_INVALID, "null argument");
     DeviceGuard guard_(h->device);
     finish_pending(h);                           // status and time of the last call (a fired watchdog shows in last_kernel_status)
-    const bool wide = !h->dense && use_wide(h);
+    const bool wide = !h->dense && use_wide(h, wrnn_wide::FMAX);
     out->ctas = h->dense ? h->dense_clusters * wrnn_dense::CL : wide ? wrnn_wide::NWORK + h->wide_nsamp : NCTA;
     out->threads = h->dense ? wrnn_dense::DTHREADS : NTHREADS;
     out->smem_bytes = h->dense ? wrnn_dense::SM_TOTAL : wide ? wrnn_wide::SM_BYTES : h->smem_bytes;

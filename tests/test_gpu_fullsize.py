@@ -134,14 +134,16 @@ def test_progress_hook_and_auto_precision():
     m = _model("RAW", "ref")
     seen = []
     m.progress = lambda done, total: seen.append((done, total))
-    m.generate(synth.make_mel(161, seed=3), True, 11000, 550, True, seed=1)              # 3 folds x 12100 steps, one launch
+    m.generate(synth.make_mel(801, seed=3), True, 11000, 550, True, seed=1)              # 14 folds x 12100 steps, one launch of the wide kernel
     m.progress = None
     assert seen and seen[-1] == (12100, 12100) and all(0 <= d <= t == 12100 for d, t in seen)
     assert [d for d, _ in seen] == sorted(d for d, _ in seen)
     # precision "auto": fp32 wide kernel for an utterance, the dense tcgen05 kernel once the pooled batch is large
     m.precision = "auto"
-    m.generate(synth.make_mel(40, seed=4), True, 700, 60, True, seed=2)
+    m.generate(synth.make_mel(60, seed=4), True, 700, 60, True, seed=2)                  # 16 folds
     assert m.last_stats["kernel_kind"] == 1
+    m.generate(synth.make_mel(25, seed=4), True, 700, 60, True, seed=2)                  # 7 folds: one group of the round-1 kernel is faster
+    assert m.last_stats["kernel_kind"] == 0
     m.generate_many([synth.make_mel(60, seed=50 + i) for i in range(12)], 700, 60, True, seed=3)   # 12 x 16 folds > 64
     assert m.last_stats["kernel_kind"] == 2
     m.precision = "fp32"
