@@ -198,6 +198,7 @@ class WaveRNN(nn.Module):
         # of materialising UpsampleNetwork's [samples, 208] output (832 B per sample).  False = materialise, as the other kernels do.
         self.expand_in_kernel = True
         self._interp_cache = None
+        self._pinned_cache = {}
         self.last_stats = {}
 
     # ------------------------------------------------------------------ teacher-forced twin (training path)
@@ -295,6 +296,14 @@ class WaveRNN(nn.Module):
                           "(or 'auto') advances them together on the tensor cores at bf16 product precision"
                           % (nfolds, self.precision, -(-nfolds // max(1, int(eng.info().max_folds_per_launch)))), RuntimeWarning, stacklevel=4)
         return eng
+
+    def _pinned(self, slot, n):
+        """Pinned float64 landing buffer number `slot` of at least n samples, kept across calls (cudaHostAlloc of a chunk's 80 MB costs
+        ~25 ms, as much as its copy); the caller gets a fresh numpy COPY of the samples, so the buffer can be reused."""
+        buf = self._pinned_cache.get(slot)
+        if buf is None or buf.numel() < n:
+            buf = self._pinned_cache[slot] = torch.empty(max(n, 1), dtype=torch.float64, pin_memory=True)
+        return buf[:n]
 
     def _dense_supported(self):
         return (self.mode == 'RAW' and self.n_classes == 512) or self.mode == 'MOL'
@@ -591,9 +600,19 @@ class WaveRNN(nn.Module):
                     host_mu = bool(mu_law) and (self.mu_law_decode == "host" or (self.mu_law_decode == "auto" and total_samples < 2_000_000))
                     fold_base = np.concatenate([[0], np.cumsum([p[0] for p in plan])])
 
+                    prep_stream = torch.cuda.Stream(device)
+
                     def prepare(ci):
-                        # Conditioning of chunk ci (PyTorch, current stream): runs on the host while the previous chunk's step loop
-                        # occupies the GPU; its kernels queue up behind that step loop.
+                        # Conditioning of chunk ci (PyTorch) on a SIDE stream: the host work overlaps the previous chunk's step loop and
+                        # its kernels run beside it (the dense kernel leaves 28 SMs free).  Copies are non-blocking: a blocking .to() of a
+                        # pinned mel waits for everything queued on its stream, i.e. for the whole step loop (measured: 515 ms per chunk).
+                        with torch.cuda.stream(prep_stream):
+                            job = prepare_on_stream(ci)
+                            job["ready"] = torch.cuda.Event()
+                            job["ready"].record(prep_stream)
+                        return job
+
+                    def prepare_on_stream(ci):
                         chunk = chunks[ci]
                         f0, f1 = int(fold_base[chunk[0]]), int(fold_base[chunk[-1] + 1])
                         job = dict(chunk=chunk, u=None if uniforms is None else uniforms[:, f0:f1].contiguous(),
@@ -602,7 +621,7 @@ class WaveRNN(nn.Module):
                             mfs, afs, geo, mb, ab = [], [], [], 0, 0
                             for i in chunk:
                                 B, L, _ = plan[i]
-                                mf, af = self.conditioning_frames(mel_list[i].to(device=device, dtype=torch.float32))
+                                mf, af = self.conditioning_frames(mel_list[i].to(device=device, dtype=torch.float32, non_blocking=True))
                                 mfs.append(mf)
                                 afs.append(af)
                                 g = np.zeros((B, 4), dtype=np.int64)
@@ -619,7 +638,7 @@ class WaveRNN(nn.Module):
                             starts, limits, base = [], [], 0
                             for i in chunk:
                                 B, L, _ = plan[i]
-                                m_up, aux = self.conditioning(mel_list[i].to(device=device, dtype=torch.float32))
+                                m_up, aux = self.conditioning(mel_list[i].to(device=device, dtype=torch.float32, non_blocking=True))
                                 if m_up.size(0) != L:
                                     raise RuntimeError("conditioning network returned %d rows, expected %d" % (m_up.size(0), L))
                                 m_all[base:base + L].copy_(m_up)
@@ -635,6 +654,9 @@ class WaveRNN(nn.Module):
                         # Enqueue the step loop of a chunk, the epilogue of each of its utterances into one device buffer, and the
                         # device-to-host copy of that buffer (pinned, on a second stream) behind them.
                         chunk = job["chunk"]
+                        main.wait_event(job["ready"])                      # the chunk's conditioning (side stream) is complete
+                        for t in (job["m"], job["a"]):
+                            t.record_stream(main)                          # allocated on the side stream, consumed on this one
                         if frames:
                             res = self._run_folds_frames(eng, device, job["m"], job["a"], job["geo"], S, job["u"], job["seed"], None, False, wait=False)
                         else:
@@ -652,34 +674,25 @@ class WaveRNN(nn.Module):
                             w0 += wave_len
                         done = torch.cuda.Event()
                         done.record(main)
-                        wav_host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+                        wav_host = self._pinned(len(jobs) % 3, n)            # three landing buffers in rotation: chunk k-2 has been collected
+                        copied = torch.cuda.Event()
                         with torch.cuda.stream(copy_stream):
                             copy_stream.wait_event(done)
                             wav_host.copy_(wav_dev, non_blocking=True)
-                        job.update(res=res, wav_dev=wav_dev, wav_host=wav_host)
+                            copied.record(copy_stream)
+                        job.update(res=res, wav_dev=wav_dev, wav_host=wav_host, copied=copied)
                         return job
 
-                    jobs, kernel_ms = [], 0.0
-                    nxt = prepare(0)
-                    for ci in range(len(chunks)):
-                        if ci > 0:
-                            kernel_ms += eng.info().last_kernel_ms          # waits for the previous chunk's step loop (as the launch below would)
-                        cur = launch(nxt)
-                        jobs.append(cur)
-                        if ci + 1 < len(chunks):
-                            nxt = prepare(ci + 1)                            # overlaps the step loop just enqueued
-                        if ci > 0:                                           # the chunk before: its step loop is done, its inputs can go
-                            for k in ("m", "a", "res", "u"):
-                                jobs[ci - 1].pop(k, None)
-                    eng.synchronize()
-                    kernel_ms += eng.info().last_kernel_ms
-                    copy_stream.synchronize()
                     outs = [None] * len(plan)
-                    for job in jobs:
+
+                    def collect(job):
+                        # host side of a finished chunk (runs while a later chunk's step loop occupies the GPU): wait for its copy,
+                        # take the utterances out of the reused pinned buffer, host mu-law decode if selected, hand them to `writer`
+                        job["copied"].synchronize()
                         flat, w0 = job["wav_host"].numpy(), 0
                         for i in job["chunk"]:
                             wave_len = plan[i][2]
-                            wav = flat[w0:w0 + wave_len]                     # a view of the chunk's pinned buffer (kept alive by numpy)
+                            wav = flat[w0:w0 + wave_len].copy()
                             if host_mu:
                                 mu = self.n_classes - 1
                                 wav = np.sign(wav) / mu * ((1 + mu) ** np.abs(wav) - 1)
@@ -688,6 +701,38 @@ class WaveRNN(nn.Module):
                             if writer is not None:
                                 writer(i, wav)
                             w0 += wave_len
+                        job.pop("wav_dev", None)
+
+                    trace = [] if os.environ.get("WRNN_TRACE") else None     # development: host timeline of the pipeline
+                    def mark(what):
+                        if trace is not None:
+                            trace.append((what, time.perf_counter()))
+                    mark("start")
+                    jobs, kernel_ms = [], 0.0
+                    nxt = prepare(0)
+                    mark("prepare 0")
+                    for ci in range(len(chunks)):
+                        if ci > 0:
+                            kernel_ms += eng.info().last_kernel_ms          # waits for the previous chunk's step loop (as the launch below would)
+                            mark("wait kernel %d" % (ci - 1))
+                        cur = launch(nxt)
+                        jobs.append(cur)
+                        mark("launch %d" % ci)
+                        if ci + 1 < len(chunks):
+                            nxt = prepare(ci + 1)                            # overlaps the step loop just enqueued
+                            mark("prepare %d" % (ci + 1))
+                        if ci > 0:                                           # the chunk before: its step loop is done, its inputs can go
+                            for k in ("m", "a", "res", "u"):
+                                jobs[ci - 1].pop(k, None)
+                            collect(jobs[ci - 1])
+                            mark("collect %d" % (ci - 1))
+                    eng.synchronize()
+                    kernel_ms += eng.info().last_kernel_ms
+                    mark("wait kernel %d" % (len(chunks) - 1))
+                    collect(jobs[-1])
+                    mark("collect %d" % (len(chunks) - 1))
+                    if trace is not None:
+                        print("generate_many timeline (ms): " + ", ".join("%s +%.1f" % (w, (t - trace[i][1]) * 1e3) for i, (w, t) in enumerate(trace[1:])), flush=True)
                     self.last_stats.update(folds=total_folds, steps=S, kernel_ms=kernel_ms, chunks=len(chunks), kernel_kind=eng.info().kernel_kind)
                     return outs
         finally:
