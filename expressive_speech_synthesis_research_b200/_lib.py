@@ -69,8 +69,8 @@ def lib():
     """Load (building first if the sources are newer) libwavernn_b200.so; raises if impossible."""
     global _LIB
     if _LIB is None:
-        path = _build.LIB
-        if _build.needs_build():
+        path = os.environ.get("WRNN_LIB") or _build.LIB          # WRNN_LIB: development knob for A/B runs of two builds on one box
+        if path == _build.LIB and _build.needs_build():
             try:
                 _build.build()
             except Exception as e:  # no nvcc on the box and no prebuilt .so
