@@ -166,7 +166,10 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                                      0 if host_mu else 20 * model.hop_length, group=group, gather_to=gather_to)
                 if wav is None:
                     return None
-                wav = wav.cpu().numpy()
+                host = model._pinned("sharded", wav.numel())            # pinned landing buffer: 106 MB of a 10-minute utterance at PCIe speed
+                host.copy_(wav, non_blocking=True)
+                torch.cuda.current_stream(device).synchronize()
+                wav = host.numpy().copy()
                 if host_mu:
                     mu = model.n_classes - 1
                     wav = np.sign(wav) / mu * ((1 + mu) ** np.abs(wav) - 1)             # decode_mu_law, dsp.py:100-105
