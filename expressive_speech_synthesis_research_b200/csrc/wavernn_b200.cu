@@ -223,7 +223,7 @@ extern "C" int32_t wrnn_create(const wrnn_config *cfg, int32_t device, wrnn_hand
                             (const void *)wrnn_wide::wavernn_wide_probe_kernel};
         for (const void *k : wk) H_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, wrnn_wide::SM_BYTES));
         int wocc = 0;
-        H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, wk[0], NTHREADS, wrnn_wide::SM_BYTES));
+        H_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, wk[0], wrnn_wide::WTHREADS, wrnn_wide::SM_BYTES));
         if (wocc >= 1) {
             h->wide = 1;
             h->wide_nsamp = prop.multiProcessorCount - wrnn_wide::NWORK;
@@ -958,7 +958,7 @@ static int32_t launch_wide(wrnn_handle *h, wrnn_wide::WParams &p, cudaStream_t s
                    : p.prof ? (mol ? (const void *)wavernn_wide_kernel_mol_prof : (const void *)wavernn_wide_kernel_prof)
                             : (mol ? (const void *)wavernn_wide_kernel_mol : (const void *)wavernn_wide_kernel);
     void *args[] = {&p};
-    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(NWORK + h->wide_nsamp), dim3(NTHREADS), args, (size_t)SM_BYTES, st));
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(NWORK + h->wide_nsamp), dim3(probe ? NTHREADS : WTHREADS), args, (size_t)SM_BYTES, st));
     h->smem_bytes = SM_BYTES;
     h->last_kernel = 1;
     h->launches += 1;
@@ -1275,7 +1275,7 @@ extern "C" int32_t wrnn_get_info(wrnn_handle *h, wrnn_info *out)
     finish_pending(h);                           // status and time of the last call (a fired watchdog shows in last_kernel_status)
     const bool wide = !h->dense && use_wide(h, wrnn_wide::FMAX);
     out->ctas = h->dense ? h->dense_clusters * wrnn_dense::CL : wide ? wrnn_wide::NWORK + h->wide_nsamp : NCTA;
-    out->threads = h->dense ? wrnn_dense::DTHREADS : NTHREADS;
+    out->threads = h->dense ? wrnn_dense::DTHREADS : wide ? wrnn_wide::WTHREADS : NTHREADS;
     out->smem_bytes = h->dense ? wrnn_dense::SM_TOTAL : wide ? wrnn_wide::SM_BYTES : h->smem_bytes;
     out->folds_per_group = h->dense ? wrnn_dense::BC : wide ? wrnn_wide::FMAX : BT;
     out->max_folds_per_launch = h->dense ? h->dense_clusters * wrnn_dense::BC : wide ? wrnn_wide::FMAX : MAXG * BT;

@@ -10,10 +10,12 @@ sys.path.insert(0, ROOT)
 from expressive_speech_synthesis_research_b200 import WaveRNN  # noqa: E402
 from oracle import synth  # noqa: E402
 
-SLOTS = ["SA wait x (sampler hop)", "SA gru1 + publish H1", "S2 gather H1", "S2 pass Wih2x + A + store + B", "S2 sum + C + gru2 + publish H2",
-         "S2 deferred (Whh1, Wfc1x) + D + finalize", "S3 deferred: warp 0 pass (Whh2)", "S3 pass Wfc1x + A + store + B", "S3 sum + C + fc1 + publish Y1",
-         "S3 deferred: D + finalize", "S3 deferred: fold halves + store", "S4 pass Wfc2 + A + store + B", "S4 sum + fc2 + publish Y2",
-         "cond: D + finalize + E", "S3 deferred: gather finish (Y1)", "S5 pass Wfc3 + A + store + B", "S5 sum + publish logits", "cond: wait for the TMA rows", "cond: pass", "S5 finalize: sum of 16 partials", "S5 gather Y2", "-", "-", "S5 finalize: bar96"]
+# pass warp 0 (thread 0): slots 0..11, 16, 17; finalize warp 0 (thread 512): 12..14; 21 = gather polls that found stale data
+SLOTS = ["P  wait: H1 published (BAR_GO)", "P  S2 gather H1 -> A", "P  S2 pass Wih2x (tensor-memory weights) + store", "P  S2 deferred Whh1 + Wfc1x (issue H2 inside) + store",
+         "P  S2 gather finish H2 -> B", "P  S3 pass Wfc1x . h2 + store", "P  S3 deferred Whh2 (issue Y1 inside) + store", "P  S3 gather finish Y1 -> A",
+         "P  S4 pass Wfc2 + store", "P  cond: TMA wait + first part", "P  S5 gather Y2 -> B", "P  S5 pass Wfc3 + store",
+         "F  wait for x (sampler round trip)", "F  arithmetic + publish (all stages)", "F  waiting for partial sums (all stages)", "-",
+         "P  cond: second part + store", "P  end-of-step barrier", "-", "-", "-", "(count) stale gather polls", "-", "-"]
 
 
 def main():
@@ -25,7 +27,7 @@ def main():
     eng = m._engine(dev)
     S = 3000
     print("exchange probe: %.3f us" % eng.measure_exchange(2000))
-    for B in (1, 8, 14, 20, 21):
+    for B in [int(a) for a in sys.argv[2:]] or (1, 8, 14, 20, 21):
         L = S + 64
         mu = torch.rand(B * L, 80, device=dev)
         au = torch.randn(B * L, 128, device=dev)
@@ -38,10 +40,8 @@ def main():
             ms = info.last_kernel_ms
             print("B=%d kernel_kind=%d profiling=%s: %.3f ms, %.2f us/step" % (B, info.kernel_kind, prof, ms, ms * 1e3 / S), flush=True)
         cyc = eng.stage_cycles().astype(np.float64) / S
-        tot = cyc[:, :21].sum(1) + cyc[:, 23]
+        tot = cyc[:, :12].sum(1) + cyc[:, 16] + cyc[:, 17]
         print("  cycles/step: cta0 total %.0f  mean %.0f  max %.0f" % (tot[0], tot.mean(), tot.max()))
-        print("  gathers (4 per step, thread 0): issue -> first answers %.0f clk each, stale poll rounds %.2f each, whole gather %.0f clk each"
-              % (cyc[:, 20].mean() / 4, cyc[:, 21].mean() / 4, cyc[:, 22].mean() / 4))
         print("  sampler of fold 0 per step: poll wait %.0f clk, logits -> x published %.0f clk, loop top (draws) %.0f clk" % (cyc[0, 24], cyc[0, 25], cyc[0, 26]))
         for i, name in enumerate(SLOTS):
             print("  %-44s cta0 %7.0f  mean %7.0f  min %7.0f  max %7.0f" % (name, cyc[0, i], cyc[:, i].mean(), cyc[:, i].min(), cyc[:, i].max()))
