@@ -11,11 +11,11 @@ from expressive_speech_synthesis_research_b200 import WaveRNN  # noqa: E402
 from oracle import synth  # noqa: E402
 
 # pass warp 0 (thread 0): slots 0..11, 16, 17; finalize warp 0 (thread 512): 12..14; 21 = gather polls that found stale data
-SLOTS = ["P  wait: H1 published (BAR_GO)", "P  S2 gather H1 -> A", "P  S2 pass Wih2x (tensor-memory weights) + store", "P  S2 deferred Whh1 + Wfc1x (issue H2 inside) + store",
+SLOTS = ["P  wait: H1 published (BAR_GO)", "P  S2 gather H1 -> A", "P  S2 pass Wih2x (tensor-memory weights) + store", "P  S2 filler Whh1 + Wfc1x (tensor memory) + issue H2 + store",
          "P  S2 gather finish H2 -> B", "P  S3 pass Wfc1x . h2 + store", "P  cond: TMA wait + part 1", "P  S3 gather Y1 -> A",
-         "P  S4 pass Wfc2 + store", "P  cond: part 2 + store", "P  S5 gather Y2 -> A", "P  S5 pass Wfc3 + store",
+         "P  S4 pass Wfc2 + store", "P  cond: part 2", "P  S5 gather Y2 -> A", "P  S5 pass Wfc3 + store",
          "F  wait for x (sampler round trip)", "F  arithmetic + publish (all stages)", "F  waiting for partial sums (all stages)", "-",
-         "P  Whh2 . h2 (end of step) + store", "P  pass-warp barrier + TMA issue", "-", "-", "-", "(count) stale gather polls", "-", "-"]
+         "P  cond part 3 + store, Whh2 . h2 + store", "P  pass-warp barrier + TMA issue", "-", "-", "-", "(count) stale gather polls", "-", "-"]
 
 
 def main():
