@@ -14,8 +14,10 @@ from oracle import synth  # noqa: E402
 SLOTS = ["P  wait: H1 published (BAR_GO)", "P  S2 gather H1 -> A", "P  S2 pass Wih2x (tensor-memory weights) + store", "P  S2 filler Whh1 + Wfc1x (tensor memory) + issue H2 + store",
          "P  S2 gather finish H2 -> B", "P  S3 pass Wfc1x . h2 + store", "P  cond: TMA wait + part 1", "P  S3 gather Y1 -> A",
          "P  S4 pass Wfc2 + store", "P  cond: part 2", "P  S5 gather Y2 -> A", "P  S5 pass Wfc3 + store",
-         "F  wait for x (sampler round trip)", "F  arithmetic + publish (all stages)", "F  waiting for partial sums (all stages)", "-",
-         "P  cond part 3 + store, Whh2 . h2 + store", "P  pass-warp barrier + TMA issue", "-", "-", "-", "(count) stale gather polls", "-", "-"]
+         "F  wait for x (sampler round trip)", "F  GRU1 + publish H1", "F  waiting for partial sums (all stages)", "-",
+         "P  cond part 3 + store, Whh2 . h2 + store", "P  pass-warp barrier + TMA issue", "-", "-", "-", "(count) stale gather polls", "-", "-",
+         "F  sum Whh2 . h2 -> gates of rnn2", "F  sum + GRU2 + publish H2", "F  sum Whh1 . h1 -> gates of rnn1, fc1 part", "F  sum + fc1 + publish Y1",
+         "F  sum + fc2 + publish Y2", "F  sum + logits sector", "F  sum conditioning projections (2 x 16 float4)", "-"]
 
 
 def main():
@@ -44,7 +46,7 @@ def main():
         print("  cycles/step: cta0 total %.0f  mean %.0f  max %.0f" % (tot[0], tot.mean(), tot.max()))
         print("  sampler of fold 0 per step: poll wait %.0f clk, logits -> x published %.0f clk, loop top (draws) %.0f clk" % (cyc[0, 24], cyc[0, 25], cyc[0, 26]))
         for i, name in enumerate(SLOTS):
-            print("  %-44s cta0 %7.0f  mean %7.0f  min %7.0f  max %7.0f" % (name, cyc[0, i], cyc[:, i].mean(), cyc[:, i].min(), cyc[:, i].max()))
+            print("  %-62s cta1 %7.0f  mean %7.0f  min %7.0f  max %7.0f" % (name, cyc[1, i], cyc[1:, i].mean(), cyc[1:, i].min(), cyc[1:, i].max()))
 
 
 if __name__ == "__main__":
