@@ -35,8 +35,9 @@ FLOP_PER_FOLD_STEP = {"RAW": 8143872, "MOL": 7650304}
 HBM_BYTES_PER_FOLD_STEP = {"RAW": 840, "MOL": 880}
 SM_CLOCK_MHZ = 1965.0
 # shared-memory operand wavefronts of one step of the wide kernel per CTA (the pipe delivers 32 lane-words
-# per clock): gate passes 16 warps x 16 k x (9 | 10 | 9), fc passes 3 x 16 x 80, conditioning 16 x 11 x 10, partial sums ~800
-WIDE_SMEM_WAVEFRONTS = 16 * 16 * (9 + 10 + 9) + 3 * 16 * 80 + 16 * 11 * 10 + 800
+# per clock): gate passes 16 warps x 16 k x (6 | 7 | 9) (Wih2x and Whh1 come from tensor memory, Whh2 from shared memory),
+# fc passes 3 x 16 x 80, conditioning 16 x 11 x 10, partial sums ~800
+WIDE_SMEM_WAVEFRONTS = 16 * 16 * (6 + 7 + 9) + 3 * 16 * 80 + 16 * 11 * 10 + 800
 SMALL_HOP_US = 0.46      # store -> successful poll of one value between two CTAs: 910 cycles (profiles/r01_l2_latency_raw.log)
 
 

@@ -20,23 +20,55 @@ def find_nvcc():
     raise RuntimeError("nvcc not found (set NVCC or put /usr/local/cuda/bin on PATH)")
 
 
+STAMP = LIB + ".stamp"
+
+
+def source_digest():
+    """sha256 of everything the library is built from (sources, headers, flags): what `needs_build` compares, so that file times
+    rewritten by a checkout or a copy to another box never trigger (or hide) a rebuild."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in DEPENDS:
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(s) > t for s in DEPENDS)
+    with open(STAMP) as f:
+        return f.read().strip() != source_digest()
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/*.cu into libwavernn_b200.so next to this file (in-tree, git-ignored)."""
+    """Compile csrc/*.cu into libwavernn_b200.so next to this file (in-tree, git-ignored).  Safe when several processes import the
+    package at once (one rank per GPU): one of them builds under a file lock into a temporary name and renames it into place, the
+    others wait for the lock and find the library current."""
+    import fcntl
     if not force and not needs_build():
         return LIB
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
-    if verbose:
-        print(res.stderr)
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            digest = source_digest()
+            tmp = "%s.tmp.%d" % (LIB, os.getpid())
+            cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
+            os.replace(tmp, LIB)
+            with open(STAMP + ".tmp", "w") as f:
+                f.write(digest + "\n")
+            os.replace(STAMP + ".tmp", STAMP)
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
