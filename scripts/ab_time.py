@@ -9,7 +9,7 @@ from oracle import synth
 dev = torch.device("cuda", 0)
 m = WaveRNN(**synth.model_kwargs("RAW", "ref")); m.load_state_dict(synth.make_state("RAW", "ref", 0)); m.cuda()
 eng = m._engine(dev)
-S = 3000
+S = int(os.environ.get("AB_STEPS", "3000"))      # AB_STEPS=40 for a compute-sanitizer pass
 out = []
 for B in [int(a) for a in sys.argv[1:]] or [1, 14, 20]:
     L = S + 64

@@ -311,3 +311,49 @@ def test_results_do_not_depend_on_the_team_layout(monkeypatch):
         monkeypatch.setenv("WRNN_FORCE_TEAMS", cap)
         got = run_folds(m, mels, aux, U, logits=True)
         assert np.array_equal(got["labels"], ref["labels"]) and np.array_equal(got["logits"], ref["logits"]), cap
+
+
+@pytest.mark.parametrize("mode", ["RAW", "MOL"])
+def test_wide_kernel_every_fold_count_and_ragged_limits(monkeypatch, mode):
+    """The wide kernel (csrc/wavernn_wide.cuh) forced for EVERY fold count 1..21 (the dispatcher only sends it more than 8): nq = 1..7
+    quads per unit, sampler warps with and without a fold, finalize threads without a quad.  A fold's samples and logits must not
+    depend on how many folds share its launch (the partial sums are added in a fixed order and handed between the pass warps and
+    the finalize warps through named barriers + a consumption counter: a lost hand-off shows up here), must match the grouped
+    round-1 kernel's logits to fp32 round-off when both are teacher-forced on the same history, and folds that run past their
+    conditioning must read zeros from then on (fatchord_version.py:306-309)."""
+    m = model(mode)
+    rng = np.random.default_rng(11)
+    B, S = 21, 48
+    mels = rng.uniform(0, 1, (B, S, 80)).astype(np.float32)
+    aux = rng.normal(0, 1, (B, S, 128)).astype(np.float32)
+    U = synth.make_uniforms(S, B, mode, seed=9).numpy()
+    monkeypatch.setenv("WRNN_KERNEL", "wide")
+    ref = run_folds(m, mels, aux, U, logits=True)
+    assert m._engine(torch.device("cuda", 0)).info().kernel_kind == 1
+    for nb in (1, 2, 3, 4, 7, 8, 9, 13, 20):
+        got = run_folds(m, mels[:nb], aux[:nb], np.ascontiguousarray(U[:, :nb]), logits=True)
+        assert np.array_equal(got["samples"], ref["samples"][:nb]), nb
+        assert np.array_equal(got["logits"], ref["logits"][:, :nb]), nb
+    # same history through the grouped kernel: logits agree to round-off (different summation trees)
+    forced = ref["samples"].T.copy()                                    # [S, B] the wide kernel's own history
+    monkeypatch.setenv("WRNN_KERNEL", "grouped")
+    grp = run_folds(m, mels, aux, U, forced=forced, logits=True)
+    assert m._engine(torch.device("cuda", 0)).info().kernel_kind == 0
+    monkeypatch.setenv("WRNN_KERNEL", "wide")
+    wid = run_folds(m, mels, aux, U, forced=forced, logits=True)
+    assert np.abs(wid["logits"] - grp["logits"]).max() <= 2e-5
+    # ragged limits: fold f has only 5 + 2 f rows of conditioning, the rest of its steps read zeros
+    dev = torch.device("cuda", 0)
+    eng = m._engine(dev)
+    mu = torch.as_tensor(mels).reshape(B * S, -1).contiguous().to(dev)
+    au = torch.as_tensor(aux).reshape(B * S, -1).contiguous().to(dev)
+    starts = np.arange(B, dtype=np.int64) * S
+    limits = starts + np.minimum(S, 5 + 2 * np.arange(B))
+    r = m._run_folds(eng, dev, mu, au, starts, limits, S, U, 0, None, True)
+    mz, az = mels.copy(), aux.copy()
+    for f in range(B):
+        mz[f, limits[f] - starts[f]:] = 0
+        az[f, limits[f] - starts[f]:] = 0
+    full = run_folds(m, mz, az, U, logits=True)
+    assert np.array_equal(r["samples"].cpu().numpy(), full["samples"])
+    assert np.array_equal(r["logits"].cpu().numpy(), full["logits"])
