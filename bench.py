@@ -278,7 +278,8 @@ def time_sentence_set(model, mels_host, dev, steps, warmup, barrier):
     step end to end from host buffers, launches per step)."""
     import torch
     mels_dev = [m.to(dev) for m in mels_host]
-    eng_launches = lambda: sum(int(e.info().launches) for e in model._engines.values())
+    eng_launches = lambda: (sum(int(e.info().launches) for e in model._engines.values())
+                            + sum(c.launches() for c in model._conds.values()))      # step-loop kernels + the frame-rate conditioning kernel
     for i in range(warmup):
         model.generate_many(mels_dev, TARGET, OVERLAP, True, seed=1000 + i)
         model.generate_many(mels_host, TARGET, OVERLAP, True, seed=1000 + i)

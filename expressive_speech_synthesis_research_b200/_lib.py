@@ -8,7 +8,7 @@ i32, i64, u64, vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_vo
 
 MODE = {"RAW": 0, "MOL": 1}
 PRECISION = {"fp32": 0, "bf16": 1, "bf16-dense": 2}
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Config(ctypes.Structure):
@@ -56,6 +56,11 @@ SYMBOLS = {
     "wrnn_set_profiling": (i32, [vp, i32]),
     "wrnn_get_stage_cycles": (i32, [vp, vp, i32]),
     "wrnn_measure_exchange": (i32, [vp, i32, ctypes.POINTER(ctypes.c_float)]),
+    "wrnn_cond_blob_floats": (i64, [i32]),
+    "wrnn_cond_create": (i32, [i32, vp, i64, i32, ctypes.POINTER(vp)]),
+    "wrnn_cond_destroy": (None, [vp]),
+    "wrnn_cond_launches": (i64, [vp]),
+    "wrnn_cond_frames": (i32, [vp, vp, vp, i32, vp, vp]),
 }
 
 _LIB = None

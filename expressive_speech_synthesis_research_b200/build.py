@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SOURCES = [os.path.join(HERE, "csrc", "wavernn_b200.cu")]
-DEPENDS = SOURCES + [os.path.join(HERE, "csrc", "wavernn_kernel.cuh"), os.path.join(HERE, "csrc", "wavernn_dense.cuh"), os.path.join(HERE, "csrc", "wavernn_wide.cuh"), os.path.join(ROOT, "include", "wavernn_b200.h")]
+DEPENDS = SOURCES + [os.path.join(HERE, "csrc", "wavernn_kernel.cuh"), os.path.join(HERE, "csrc", "wavernn_dense.cuh"), os.path.join(HERE, "csrc", "wavernn_wide.cuh"), os.path.join(HERE, "csrc", "wavernn_cond.cuh"), os.path.join(ROOT, "include", "wavernn_b200.h")]
 LIB = os.path.join(HERE, "libwavernn_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

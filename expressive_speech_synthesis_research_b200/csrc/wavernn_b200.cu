@@ -4,6 +4,7 @@
 #include "wavernn_kernel.cuh"
 #include "wavernn_dense.cuh"
 #include "wavernn_wide.cuh"
+#include "wavernn_cond.cuh"
 
 #include <atomic>
 #include <cmath>
@@ -1422,4 +1423,110 @@ extern "C" int32_t wrnn_xfade_unfold_segment(const float *samples, int32_t num_r
                                              double *out, void *stream)
 {
     return xfade_impl(samples, num_rows, steps, 1, overlap, mu_law_classes, wave_len, tail_fade, first_fold, total_folds, seg_start, seg_len, out, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MelResNet at frame rate (csrc/wavernn_cond.cuh): one object per (device, model), independent of the step-loop engines
+// ---------------------------------------------------------------------------------------------
+struct wrnn_cond {
+    int device = 0, res_blocks = 0;
+    float *blob = nullptr;
+    wrnn_mel::Tile *tiles_dev = nullptr, *tiles_host = nullptr;    // device table | pinned staging
+    int tiles_cap = 0;
+    cudaEvent_t copied = nullptr;                                   // the staging buffer has been read by the last call's copy
+    int64_t launches = 0;
+};
+
+extern "C" int64_t wrnn_cond_blob_floats(int32_t res_blocks) { return res_blocks < 0 ? -1 : (int64_t)wrnn_mel::blob_floats(res_blocks); }
+
+extern "C" int32_t wrnn_cond_create(int32_t device, const float *blob_host, int64_t n_floats, int32_t res_blocks, wrnn_cond **out)
+{
+    if (!blob_host || !out || res_blocks < 0) return fail(WRNN_ERR_INVALID, "wrnn_cond_create: null argument");
+    if (n_floats != (int64_t)wrnn_mel::blob_floats(res_blocks))
+        return fail(WRNN_ERR_INVALID, "wrnn_cond_create: blob has %lld floats, %lld expected for %d residual blocks (80 x 5 -> 128 -> 128 only)",
+                    (long long)n_floats, (long long)wrnn_mel::blob_floats(res_blocks), res_blocks);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if ((int)prop.sharedMemPerBlockOptin < wrnn_mel::SM_BYTES) return fail(WRNN_ERR_INVALID, "wrnn_cond_create: device offers %d bytes of shared memory, %d needed", (int)prop.sharedMemPerBlockOptin, wrnn_mel::SM_BYTES);
+    wrnn_cond *c = new wrnn_cond;
+    c->device = device;
+    c->res_blocks = res_blocks;
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&c->blob, (size_t)n_floats * sizeof(float))) != cudaSuccess ||
+        (e = cudaMemcpy(c->blob, blob_host, (size_t)n_floats * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c->copied, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaFuncSetAttribute(wrnn_mel::wavernn_melresnet_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wrnn_mel::SM_BYTES)) != cudaSuccess) {
+        cudaFree(c->blob);
+        if (c->copied) cudaEventDestroy(c->copied);
+        delete c;
+        return fail(WRNN_ERR_CUDA, "wrnn_cond_create: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return WRNN_OK;
+}
+
+extern "C" void wrnn_cond_destroy(wrnn_cond *c)
+{
+    if (!c) return;
+    DeviceGuard guard(c->device);
+    cudaFree(c->blob);
+    cudaFree(c->tiles_dev);
+    cudaFreeHost(c->tiles_host);
+    if (c->copied) cudaEventDestroy(c->copied);
+    delete c;
+}
+
+extern "C" int64_t wrnn_cond_launches(const wrnn_cond *c) { return c ? c->launches : -1; }
+
+// segments [nseg][3] (host): {first row of the segment's zero-padded mel frames in `mel_frames`, output frames T (the segment has
+// T + 4 input rows), first output row in `aux_out`}.  Enqueues on `stream` and returns.
+extern "C" int32_t wrnn_cond_frames(wrnn_cond *c, const float *mel_frames, const int32_t *segments, int32_t nseg, float *aux_out, void *stream)
+{
+    using namespace wrnn_mel;
+    if (!c || !mel_frames || !segments || !aux_out || nseg < 0) return fail(WRNN_ERR_INVALID, "wrnn_cond_frames: null argument");
+    DeviceGuard guard(c->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int ntiles = 0;
+    for (int s = 0; s < nseg; ++s) {
+        if (segments[3 * s + 1] < 0 || segments[3 * s] < 0 || segments[3 * s + 2] < 0) return fail(WRNN_ERR_INVALID, "wrnn_cond_frames: negative segment field");
+        ntiles += (segments[3 * s + 1] + TF - 1) / TF;
+    }
+    if (ntiles == 0) return WRNN_OK;
+    if (ntiles > c->tiles_cap) {
+        CUDA_TRY(cudaEventSynchronize(c->copied));
+        cudaFree(c->tiles_dev);
+        cudaFreeHost(c->tiles_host);
+        c->tiles_dev = nullptr;
+        c->tiles_host = nullptr;
+        c->tiles_cap = 0;
+        const int cap = ntiles + ntiles / 2 + 64;
+        CUDA_TRY(cudaMalloc(&c->tiles_dev, (size_t)cap * sizeof(Tile)));
+        CUDA_TRY(cudaMallocHost(&c->tiles_host, (size_t)cap * sizeof(Tile)));
+        c->tiles_cap = cap;
+    }
+    CUDA_TRY(cudaEventSynchronize(c->copied));             // the previous call's copy has read the staging buffer (normally long ago)
+    int k = 0;
+    for (int s = 0; s < nseg; ++s) {
+        const int row0 = segments[3 * s], T = segments[3 * s + 1], out0 = segments[3 * s + 2];
+        for (int f = 0; f < T; f += TF, ++k) {
+            Tile &t = c->tiles_host[k];
+            t.mel_row0 = row0 + f;
+            t.mel_rows = T + KS - 1 - f;                   // rows of the segment from this tile's first input row on
+            t.out_row0 = out0 + f;
+            t.nvalid = T - f < TF ? T - f : TF;
+        }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->tiles_dev, c->tiles_host, (size_t)ntiles * sizeof(Tile), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaEventRecord(c->copied, st));
+    MParams p;
+    p.blob = c->blob;
+    p.mel = mel_frames;
+    p.aux = aux_out;
+    p.tiles = c->tiles_dev;
+    p.res_blocks = c->res_blocks;
+    wavernn_melresnet_kernel<<<ntiles, NT, SM_BYTES, st>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    c->launches += 1;
+    return WRNN_OK;
 }

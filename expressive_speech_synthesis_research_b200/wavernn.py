@@ -154,6 +154,36 @@ class _Engine:
             pass
 
 
+class _Cond:
+    """Owns one wrnn_cond (include/wavernn_b200.h): the frame-rate MelResNet of one model on one CUDA device."""
+
+    def __init__(self, blob: np.ndarray, res_blocks: int, device_index: int):
+        self.lib = _lib.lib()
+        self.handle = _lib.vp()
+        self.device_index = device_index
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        _lib.check(self.lib.wrnn_cond_create(device_index, blob.ctypes.data_as(ctypes.c_void_p), blob.size, res_blocks, ctypes.byref(self.handle)))
+        self.tag = None
+
+    def launches(self):
+        return int(self.lib.wrnn_cond_launches(self.handle))
+
+    def frames(self, mel_frames, segments, aux_out):
+        """mel_frames [rows, 80] (device, zero-padded segments), segments int32 [n, 3] host, aux_out [rows, 128] (device): one launch."""
+        seg = np.ascontiguousarray(segments, dtype=np.int32)
+        stream = torch.cuda.current_stream(mel_frames.device).cuda_stream
+        _lib.check(self.lib.wrnn_cond_frames(self.handle, ctypes.c_void_p(mel_frames.data_ptr()), seg.ctypes.data_as(ctypes.c_void_p),
+                                             seg.shape[0], ctypes.c_void_p(aux_out.data_ptr()), ctypes.c_void_p(stream)))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.wrnn_cond_destroy(self.handle)
+                self.handle = _lib.vp()
+        except Exception:
+            pass
+
+
 class WaveRNN(nn.Module):
     """Drop-in for models.fatchord_version.WaveRNN on the generation path."""
 
@@ -185,6 +215,7 @@ class WaveRNN(nn.Module):
         self._feat_dims = feat_dims
         self._fc_dims = fc_dims
         self._engines = {}
+        self._conds = {}                    # device index -> _Cond (frame-rate MelResNet kernel)
         # "fp32" (default, the reference's precision) or "bf16": resident weights rounded to bf16 (after the fp64
         # folding of the input layer), activations and accumulation stay fp32.  Set before calling generate().
         self.precision = "fp32"
@@ -297,12 +328,21 @@ class WaveRNN(nn.Module):
                           % (nfolds, self.precision, -(-nfolds // max(1, int(eng.info().max_folds_per_launch)))), RuntimeWarning, stacklevel=4)
         return eng
 
-    def _pinned(self, slot, n):
-        """Pinned float64 landing buffer number `slot` of at least n samples, kept across calls (cudaHostAlloc of a chunk's 80 MB costs
+    def _side_stream(self, device, name):
+        """Side streams are kept across calls: the caching allocator keeps a pool per stream, and a fresh stream per call starts
+        with an empty one (cudaMalloc for every conditioning tensor: ~20 ms per generate_many call)."""
+        key = ("stream", name, device.index if device.index is not None else torch.cuda.current_device())
+        st = self._pinned_cache.get(key)
+        if st is None:
+            st = self._pinned_cache[key] = torch.cuda.Stream(device)
+        return st
+
+    def _pinned(self, slot, n, dtype=torch.float64):
+        """Pinned buffer number `slot` of at least n elements, kept across calls (cudaHostAlloc of a chunk's 80 MB costs
         ~25 ms, as much as its copy); the caller gets a fresh numpy COPY of the samples, so the buffer can be reused."""
         buf = self._pinned_cache.get(slot)
-        if buf is None or buf.numel() < n:
-            buf = self._pinned_cache[slot] = torch.empty(max(n, 1), dtype=torch.float64, pin_memory=True)
+        if buf is None or buf.numel() < n or buf.dtype != dtype:
+            buf = self._pinned_cache[slot] = torch.empty(max(n, 1), dtype=dtype, pin_memory=True)
         return buf[:n]
 
     def _dense_supported(self):
@@ -344,9 +384,86 @@ class WaveRNN(nn.Module):
         self._interp_cache = (tag, table)
         return table
 
+    # ------------------------------------------------------------------ frame-rate conditioning (csrc/wavernn_cond.cuh)
+    MELRESNET_KEYS = ("conv_in.weight", "batch_norm.weight", "batch_norm.bias", "batch_norm.running_mean", "batch_norm.running_var",
+                      "conv_out.weight", "conv_out.bias")
+
+    def melresnet_native(self):
+        """True when the MelResNet has the reference's dimensions (hparams.py:35-39: 80 mel channels, kernel 2 pad + 1 = 5, 128 compute
+        and output channels), which is what the CUDA kernel is written for; other shapes run through PyTorch on the GPU."""
+        rn = self.upsample.resnet
+        return (rn.conv_in.in_channels == 80 and rn.conv_in.kernel_size[0] == 5 and rn.conv_in.out_channels == 128
+                and rn.conv_out.out_channels == 128 and self.pad == 2 and os.environ.get("WRNN_MELRESNET", "native") != "torch")
+
+    def pack_melresnet(self):
+        """The weight blob of wrnn_cond_create (layout: include/wavernn_b200.h): convolution weights transposed to [in][out], eval-mode
+        batch norm (fatchord_version.py:13-24, 36-44) folded in float64 to scale = w / sqrt(var + eps), shift = b - mean * scale."""
+        rn = self.upsample.resnet
+        sd = {k: v.detach().to("cpu", torch.float64).numpy() for k, v in rn.state_dict().items() if v.is_floating_point()}
+
+        def bn(prefix, eps):
+            scale = sd[prefix + ".weight"] / np.sqrt(sd[prefix + ".running_var"] + eps)
+            return [scale, sd[prefix + ".bias"] - sd[prefix + ".running_mean"] * scale]
+
+        parts = [sd["conv_in.weight"].transpose(2, 1, 0).reshape(-1)] + bn("batch_norm", rn.batch_norm.eps)     # [tap][in][out]
+        for i, layer in enumerate(rn.layers):
+            parts += [sd["layers.%d.conv1.weight" % i][:, :, 0].T.reshape(-1)] + bn("layers.%d.batch_norm1" % i, layer.batch_norm1.eps)
+            parts += [sd["layers.%d.conv2.weight" % i][:, :, 0].T.reshape(-1)] + bn("layers.%d.batch_norm2" % i, layer.batch_norm2.eps)
+        parts += [sd["conv_out.weight"][:, :, 0].T.reshape(-1), sd["conv_out.bias"]]
+        return np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1) for x in parts]).astype(np.float32)
+
+    def _cond(self, device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        c = self._conds.get(idx)
+        sd = self.upsample.resnet.state_dict()
+        tag = tuple((v.data_ptr(), v._version) for v in sd.values())
+        if c is None or c.tag != tag:
+            with torch.cuda.device(idx):
+                c = self._conds[idx] = _Cond(self.pack_melresnet(), len(self.upsample.resnet.layers), idx)
+            c.tag = tag
+        return c
+
+    def conditioning_frames_many(self, mel_list, device):
+        """Frame-rate prologue of SEVERAL utterances in one host-to-device copy and one kernel launch:
+        [(1, feat, T_i)] -> mel frames [sum (T_i + 2 pad), feat] (zero-padded per utterance), MelResNet output [sum T_i, 4 aux],
+        row offsets of every utterance in both.  A frame's result does not depend on what it is pooled with."""
+        Ts = [int(m.shape[-1]) for m in mel_list]
+        mel_rows = np.concatenate([[0], np.cumsum([T + 2 * self.pad for T in Ts])]).astype(np.int64)
+        aux_rows = np.concatenate([[0], np.cumsum(Ts)]).astype(np.int64)
+        af = torch.empty(int(aux_rows[-1]), 4 * self.aux_dims, dtype=torch.float32, device=device)
+        seg = np.stack([mel_rows[:-1], np.asarray(Ts, dtype=np.int64), aux_rows[:-1]], axis=1)
+        if all(m.is_cuda for m in mel_list):                       # inputs already resident in HBM: assemble on the device
+            mf = torch.zeros(int(mel_rows[-1]), self._feat_dims, dtype=torch.float32, device=device)
+            for i, m in enumerate(mel_list):
+                mf[mel_rows[i] + self.pad: mel_rows[i] + self.pad + Ts[i]].copy_(m.detach()[0].t())
+            self._cond(device).frames(mf, seg, af)
+            return mf, af, mel_rows, aux_rows
+        host = self._pinned("cond_frames", int(mel_rows[-1]) * self._feat_dims, dtype=torch.float32).view(int(mel_rows[-1]), self._feat_dims)
+        hv = host.numpy()
+        ev = self._pinned_cache.get("cond_frames_event")
+        if ev is not None:
+            ev.synchronize()                       # the previous call's copy has read the staging buffer
+        hv[:] = 0.0
+        for i, m in enumerate(mel_list):
+            mm = m.detach()
+            if mm.is_cuda:
+                mm = mm.cpu()
+            hv[mel_rows[i] + self.pad: mel_rows[i] + self.pad + Ts[i]] = mm.to(torch.float32).numpy()[0].T
+        mf = host.to(device, non_blocking=True)
+        ev = self._pinned_cache["cond_frames_event"] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self._cond(device).frames(mf, seg, af)
+        return mf, af, mel_rows, aux_rows
+
     def conditioning_frames(self, mels):
         """Frame-rate view of the prologue (fatchord_version.py:162-165) for the in-kernel expansion:
         (1, feat, T) -> zero-padded mel frames [T + 2*pad, feat] and MelResNet output [T, 4*aux]."""
+        if mels.is_cuda and self.melresnet_native():
+            m = F.pad(mels.to(torch.float32), (self.pad, self.pad))[0].t().contiguous()
+            T = int(mels.shape[-1])
+            aux = torch.empty(T, 4 * self.aux_dims, dtype=torch.float32, device=mels.device)
+            self._cond(mels.device).frames(m, np.array([[0, T, 0]], dtype=np.int32), aux)
+            return m, aux
         m = F.pad(mels, (self.pad, self.pad))
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             prev = torch.backends.cuda.matmul.allow_tf32
@@ -593,14 +710,14 @@ class WaveRNN(nn.Module):
                         chunks.append(cur)
                     frames = self._frames_mode(eng)
                     main = torch.cuda.current_stream(device)
-                    copy_stream = torch.cuda.Stream(device)
+                    copy_stream = self._side_stream(device, "copy")
                     if self.mu_law_decode not in ("auto", "host", "device"):
                         raise ValueError("mu_law_decode must be 'auto', 'host' or 'device', got %r" % (self.mu_law_decode,))
                     total_samples = sum(p[2] for p in plan)
                     host_mu = bool(mu_law) and (self.mu_law_decode == "host" or (self.mu_law_decode == "auto" and total_samples < 2_000_000))
                     fold_base = np.concatenate([[0], np.cumsum([p[0] for p in plan])])
 
-                    prep_stream = torch.cuda.Stream(device)
+                    prep_stream = self._side_stream(device, "prep")
 
                     def prepare(ci):
                         # Conditioning of chunk ci (PyTorch) on a SIDE stream: the host work overlaps the previous chunk's step loop and
@@ -617,7 +734,17 @@ class WaveRNN(nn.Module):
                         f0, f1 = int(fold_base[chunk[0]]), int(fold_base[chunk[-1] + 1])
                         job = dict(chunk=chunk, u=None if uniforms is None else uniforms[:, f0:f1].contiguous(),
                                    seed=None if seed is None else int(seed) + ci)          # in-kernel draws: one Philox stream per chunk
-                        if frames:
+                        if frames and self.melresnet_native():
+                            mf, af, mrows, arows = self.conditioning_frames_many([mel_list[i] for i in chunk], device)
+                            geo = []
+                            for j, i in enumerate(chunk):
+                                B, L, _ = plan[i]
+                                g = np.zeros((B, 4), dtype=np.int64)
+                                g[:, 0] = np.arange(B, dtype=np.int64) * (target + overlap)
+                                g[:, 1], g[:, 2], g[:, 3] = L, mrows[j], arows[j]
+                                geo.append(g)
+                            job.update(m=mf, a=af, geo=np.concatenate(geo))
+                        elif frames:
                             mfs, afs, geo, mb, ab = [], [], [], 0, 0
                             for i in chunk:
                                 B, L, _ = plan[i]

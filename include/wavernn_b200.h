@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WRNN_ABI_VERSION 2
+#define WRNN_ABI_VERSION 3
 
 typedef enum {
     WRNN_OK = 0,
@@ -229,6 +229,27 @@ int32_t wrnn_get_stage_cycles(wrnn_handle *h, int64_t *out /* [host] */, int32_t
  * kernel: 32 {value, epoch} pairs published, 4096 gathered), `iters` times on an otherwise empty persistent kernel.
  * Writes the mean device time per exchange in microseconds.  Synchronous. */
 int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *usec_per_exchange);
+
+/* ---- frame-rate conditioning network (csrc/wavernn_cond.cuh) -------------------------------------------------------
+ * Replaces: MelResNet.forward, WaveRNN/models/fatchord_version.py:28-45 (ResBlock :10-25): the `aux` half of
+ * UpsampleNetwork.forward (:79-86) before Stretch2d repeats it.  Dimensions are the reference's (hparams.py:35-39):
+ * 80 mel channels, kernel 5, 128 compute / output channels; `res_blocks` is free.  Eval-mode batch norm arrives folded:
+ * blob (host floats, wrnn_cond_blob_floats(res_blocks) of them) =
+ *   W0 [5 taps][80 in][128 out] | scale0 [128] | shift0 [128] |
+ *   res_blocks x { W1 [128 in][128 out] | scale1 | shift1 | W2 [128 in][128 out] | scale2 | shift2 } | Wout [128 in][128 out] | bias [128]
+ * (WaveRNN.pack_melresnet builds it from the state_dict in float64).  One object per device and model; not tied to an engine. */
+typedef struct wrnn_cond wrnn_cond;
+int64_t wrnn_cond_blob_floats(int32_t res_blocks);
+int32_t wrnn_cond_create(int32_t device, const float *blob_host, int64_t n_floats, int32_t res_blocks, wrnn_cond **out);
+void wrnn_cond_destroy(wrnn_cond *c);
+/* kernels launched by this object so far (bench.py's gpu_launches) */
+int64_t wrnn_cond_launches(const wrnn_cond *c);
+/* aux = MelResNet(mel) for `nseg` utterances in ONE launch.  mel_frames (device) [rows][80]: every segment's mel frames, already
+ * zero-padded by `pad` = 2 frames on both sides (fatchord_version.py:164); segments (HOST) [nseg][3] int32 =
+ * {first row of the segment in mel_frames, T = frames out (the segment has T + 4 rows), first row of its output in aux_out};
+ * aux_out (device) [rows][128].  A frame's result does not depend on the segment or launch it shares.  Enqueues on `stream`
+ * (cudaStream_t) and returns. */
+int32_t wrnn_cond_frames(wrnn_cond *c, const float *mel_frames, const int32_t *segments, int32_t nseg, float *aux_out, void *stream);
 
 #ifdef __cplusplus
 }

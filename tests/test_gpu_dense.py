@@ -218,3 +218,31 @@ def test_dense_edge_cases_fold_counts_and_short_runs():
     end), the shortest legal utterance through generate(): no watchdog, finite logits, labels consistent with the kernel's logits."""
     from scripts import dense_edge_sweep
     assert dense_edge_sweep.main() == 0
+
+
+def test_native_melresnet_matches_torch_and_pooling_is_bit_identical():
+    """a2 (MelResNet.forward, fatchord_version.py:28-45) as csrc/wavernn_cond.cuh: within fp32 round-off of the PyTorch network, and a
+    frame's result independent of the utterances it is pooled with (one launch, tiles of 64 frames; per-utterance cuDNN calls do not
+    promise that across shapes)."""
+    from tests.test_melresnet_pack import replay
+    m = WaveRNN(**synth.model_kwargs("RAW", "fatchord"))
+    m.load_state_dict(synth.make_state("RAW", "fatchord", 0))
+    m = m.cuda()
+    m.eval()
+    dev = torch.device("cuda", 0)
+    assert m.melresnet_native()
+    mels = [synth.make_mel(T, seed=70 + T) for T in (21, 64, 65, 130, 803)]
+    mf, af, mrows, arows = m.conditioning_frames_many(mels, dev)
+    torch.cuda.synchronize()
+    blob, nb = m.pack_melresnet(), len(m.upsample.resnet.layers)
+    for i, mel in enumerate(mels):
+        T = mel.shape[-1]
+        single_m, single_a = m.conditioning_frames(mel.to(dev))
+        assert torch.equal(single_m, mf[mrows[i]:mrows[i + 1]])
+        assert torch.equal(single_a, af[arows[i]:arows[i + 1]]), T          # bit-identical whatever the pooling
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            want = m.upsample.resnet(torch.nn.functional.pad(mel.to(dev), (2, 2)))[0].t()
+        err = float((single_a - want).abs().max())
+        assert err <= 2e-5 * max(1.0, float(want.abs().max())), (T, err)
+        rep = replay(blob, single_m.cpu().numpy(), nb)
+        assert np.abs(rep - single_a.cpu().numpy()).max() <= 2e-5 * max(1.0, float(want.abs().max()))
