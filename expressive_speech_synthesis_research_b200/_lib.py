@@ -56,6 +56,7 @@ SYMBOLS = {
     "wrnn_set_profiling": (i32, [vp, i32]),
     "wrnn_get_stage_cycles": (i32, [vp, vp, i32]),
     "wrnn_measure_exchange": (i32, [vp, i32, ctypes.POINTER(ctypes.c_float)]),
+    "wrnn_set_kernel": (i32, [vp, i32]),
     "wrnn_cond_blob_floats": (i64, [i32]),
     "wrnn_cond_create": (i32, [i32, vp, i64, i32, ctypes.POINTER(vp)]),
     "wrnn_cond_destroy": (None, [vp]),

@@ -61,6 +61,7 @@ struct wrnn_handle {
     // wide kernel (csrc/wavernn_wide.cuh): all folds of a launch through one exchange per stage; fp32 RAW-512 / MOL
     int wide = 0, wide_nsamp = 0;
     int last_kernel = 0;                  // 0 grouped (round-1) kernel, 1 wide kernel, 2 dense kernel
+    int kernel_choice = -1;               // wrnn_set_kernel: -1 by fold count, 0 grouped, 1 wide
     float *wide_img = nullptr;            // [NWORK][IMG_FLOATS]
     unsigned *wide_xb = nullptr;          // XW_TOTAL words
     int *progress_host = nullptr, *progress_dev = nullptr;   // mapped step counter (wrnn_progress)
@@ -971,6 +972,8 @@ static int32_t launch_wide(wrnn_handle *h, wrnn_wide::WParams &p, cudaStream_t s
 static bool use_wide(const wrnn_handle *h, int num_folds)
 {
     if (!h->wide) return false;
+    if (h->kernel_choice == 0) return false;
+    if (h->kernel_choice == 1) return true;
     const char *k = getenv("WRNN_KERNEL");
     if (k && strcmp(k, "grouped") == 0) return false;
     if (k && strcmp(k, "wide") == 0) return true;
@@ -1436,6 +1439,13 @@ struct wrnn_cond {
     cudaEvent_t copied = nullptr;                                   // the staging buffer has been read by the last call's copy
     int64_t launches = 0;
 };
+
+extern "C" int32_t wrnn_set_kernel(wrnn_handle *h, int32_t choice)
+{
+    if (!h || choice < -1 || choice > 1) return fail(WRNN_ERR_INVALID, "wrnn_set_kernel: choice must be -1 (by fold count), 0 (grouped) or 1 (wide)");
+    h->kernel_choice = choice;
+    return WRNN_OK;
+}
 
 extern "C" int64_t wrnn_cond_blob_floats(int32_t res_blocks) { return res_blocks < 0 ? -1 : (int64_t)wrnn_mel::blob_floats(res_blocks); }
 

@@ -147,18 +147,29 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                 B, _ = _lib.fold_index(L, target, overlap)
                 S = target + 2 * overlap
                 lo, hi = fold_ranges(B, world)[rank]
+                # the fp32 kernels differ in summation order: every rank runs the one the unsplit call would run (by ALL B folds)
+                eng.set_kernel(1 if B > 8 else 0)
                 if hi > lo:
                     starts = np.arange(lo, hi, dtype=np.int64) * (target + overlap)
                     u = None if uniforms is None else torch.as_tensor(uniforms)[:, lo:hi]
                     if frames:
                         geo = np.stack([starts, np.full(hi - lo, L), np.zeros(hi - lo), np.zeros(hi - lo)], axis=1)
-                        res = model._run_folds_frames(eng, device, mel_fr, aux_fr, geo, S, u, seed + rank, None, False)
+                        res = model._run_folds_frames(eng, device, mel_fr, aux_fr, geo, S, u, seed + rank, None, False, wait=False)
                     else:
                         limits = np.full(hi - lo, L, dtype=np.int64)
-                        res = model._run_folds(eng, device, m_up, aux, starts, limits, S, u, seed + rank, None, False)
+                        res = model._run_folds(eng, device, m_up, aux, starts, limits, S, u, seed + rank, None, False, wait=False)
                     local = res["samples"]
                 else:
                     local = torch.empty(0, S, dtype=torch.float32, device=device)
+                # The step loop is running (the calls above only enqueue).  The root uses the wait to get the caller's array ready: a
+                # fresh 106 MB array (10-minute utterance) costs ~20 ms of page faults when it is first written.
+                out = None
+                if gather_to is not None and rank == gather_to:
+                    out = np.empty(wave_len, dtype=np.float64)
+                    out[::512] = 0.0                                              # touch every 4 KB page
+                    model._pinned("sharded", wave_len)
+                if hi > lo:
+                    eng.synchronize()                                             # watchdog status of the step loop
                 # same decode policy as WaveRNN.generate: bit-exact numpy mu-law + tail fade on the host below 2 M samples
                 host_mu = bool(mu_law) and gather_to is not None and (
                     model.mu_law_decode == "host" or (model.mu_law_decode == "auto" and wave_len < 2_000_000))
@@ -169,11 +180,16 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                 host = model._pinned("sharded", wav.numel())            # pinned landing buffer: 106 MB of a 10-minute utterance at PCIe speed
                 host.copy_(wav, non_blocking=True)
                 torch.cuda.current_stream(device).synchronize()
-                wav = host.numpy().copy()
+                if out is None or out.size != wav.numel():
+                    out = np.empty(wav.numel(), dtype=np.float64)
+                torch.from_numpy(out).copy_(host)                       # multi-threaded copy into the pre-faulted array
+                wav = out
                 if host_mu:
                     mu = model.n_classes - 1
                     wav = np.sign(wav) / mu * ((1 + mu) ** np.abs(wav) - 1)             # decode_mu_law, dsp.py:100-105
                     wav[-20 * model.hop_length:] *= np.linspace(1, 0, 20 * model.hop_length)   # fatchord_version.py:235-237
                 return wav
     finally:
+        for e in model._engines.values():
+            e.set_kernel(-1)                      # back to the per-call choice
         model.train()

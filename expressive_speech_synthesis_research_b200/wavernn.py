@@ -117,6 +117,10 @@ class _Engine:
         _lib.check(self.lib.wrnn_get_info(self.handle, ctypes.byref(out)))
         return out
 
+    def set_kernel(self, choice):
+        """-1: fp32 kernel by the fold count of each call (default); 0 grouped; 1 wide (wrnn_set_kernel)."""
+        _lib.check(self.lib.wrnn_set_kernel(self.handle, int(choice)))
+
     def synchronize(self):
         """Wait for the generate call enqueued last; raises when an in-kernel watchdog fired (WRNN_ERR_TIMEOUT)."""
         _lib.check(self.lib.wrnn_synchronize(self.handle))
