@@ -139,8 +139,25 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                 wave_len = (mels.size(-1) - 1) * model.hop_length
                 frames = model._frames_mode(eng)              # dense kernel: conditioning expanded in the kernel, as generate() does
                 if frames:
-                    mel_fr, aux_fr = model.conditioning_frames(mels)
                     L = mels.size(-1) * model.hop_length
+                    if model.melresnet_native():
+                        # the conditioning network is sharded with the folds.  A rank's folds read the samples
+                        # [lo (t + o), hi (t + o) + o), i.e. aux frames [p0 / hop, (p1 - 1) / hop]; the MelResNet kernel computes exactly
+                        # those (its k = 5 input window is the halo), and a frame's result does not depend on what is computed with it
+                        # (csrc/wavernn_cond.cuh), so the shards are bit-identical to the unsplit run.  The zero-padded mel frames
+                        # themselves (a transpose) are kept whole: the kernel's box-filter taps index them directly.
+                        import torch.nn.functional as F
+                        T = int(mels.size(-1))
+                        mel_fr = F.pad(mels, (model.pad, model.pad))[0].t().contiguous()
+                        aux_fr = torch.zeros(T, 4 * model.aux_dims, dtype=torch.float32, device=device)
+                        Bt, _ = _lib.fold_index(L, target, overlap)
+                        flo, fhi = fold_ranges(Bt, world)[rank]
+                        if fhi > flo:
+                            p0, p1 = flo * (target + overlap), min(L, fhi * (target + overlap) + overlap)
+                            a0, a1 = p0 // model.hop_length, min(T - 1, (p1 - 1) // model.hop_length)
+                            model._cond(device).frames(mel_fr, np.array([[a0, a1 - a0 + 1, a0]], dtype=np.int32), aux_fr)
+                    else:
+                        mel_fr, aux_fr = model.conditioning_frames(mels)
                 else:
                     m_up, aux = model.conditioning(mels)
                     L = m_up.size(0)
