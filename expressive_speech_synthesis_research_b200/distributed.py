@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from .wavio import decode_mu_law_host
 
 
 def plan_utterances(fold_counts, world_size):
@@ -203,7 +204,7 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                 wav = out
                 if host_mu:
                     mu = model.n_classes - 1
-                    wav = np.sign(wav) / mu * ((1 + mu) ** np.abs(wav) - 1)             # decode_mu_law, dsp.py:100-105
+                    wav = decode_mu_law_host(wav, mu)             # decode_mu_law, dsp.py:100-105
                     wav[-20 * model.hop_length:] *= np.linspace(1, 0, 20 * model.hop_length)   # fatchord_version.py:235-237
                 return wav
     finally:

@@ -20,7 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib
-from .wavio import WavWriter, save_wav
+from .wavio import WavWriter, decode_mu_law_host, save_wav
 
 
 class _ResidualUnit(nn.Module):
@@ -559,7 +559,7 @@ class WaveRNN(nn.Module):
             # decode_mu_law (dsp.py:100-105) and the tail fade (fatchord_version.py:235-237) with the reference's own numpy
             # expressions on the crossfaded float64 signal: bit-exact, where CUDA's pow is within 2 ulp of numpy's
             mu = self.n_classes - 1
-            wav = np.sign(wav) / mu * ((1 + mu) ** np.abs(wav) - 1)
+            wav = decode_mu_law_host(wav, mu)
             wav[-20 * self.hop_length:] *= np.linspace(1, 0, 20 * self.hop_length)
         self.last_stats["wall_s"] = time.perf_counter() - t_start
         if save_path is not None:
@@ -826,7 +826,7 @@ class WaveRNN(nn.Module):
                             wav = flat[w0:w0 + wave_len].copy()
                             if host_mu:
                                 mu = self.n_classes - 1
-                                wav = np.sign(wav) / mu * ((1 + mu) ** np.abs(wav) - 1)
+                                wav = decode_mu_law_host(wav, mu)
                                 wav[-20 * self.hop_length:] *= np.linspace(1, 0, 20 * self.hop_length)
                             outs[i] = wav
                             if writer is not None:

@@ -2,6 +2,7 @@
 save_wav used (WaveRNN/utility/dsp.py:21-22 float32; fatchord_version.py:239) and for its 16-bit path (encode_16bits,
 dsp.py:36-37; synthesize_sentences.py:72 writes int16 through scipy).  `WavWriter` streams: generate_many hands every
 utterance over as soon as its epilogue has landed, so a sentence set never sits in memory as a whole."""
+import os
 import struct
 
 import numpy as np
@@ -85,3 +86,36 @@ def load_wav(path):
             data = np.frombuffer(chunk, dtype='<f4' if (tag_fmt, bits) == (3, 32) else '<i2').copy()
         pos += 8 + size + (size & 1)
     return data, rate
+
+
+# ---------------------------------------------------------------------------------------------
+# bit-exact mu-law expansion on the host
+# ---------------------------------------------------------------------------------------------
+_DECODE_POOL = None
+
+
+def decode_mu_law_host(y, mu):
+    """decode_mu_law(y, mu + 1, from_labels=False), WaveRNN/utility/dsp.py:100-105, with numpy's own float64 `pow`: the expression
+    is the reference's, evaluated slice by slice on a few threads (numpy releases the GIL inside the ufuncs; 220 000 samples cost
+    5 ms on one thread, as much as 400 steps of the kernel).  Every slice but the last is a multiple of 64 elements long, so each
+    element goes through the same vector / scalar loop of numpy as in one big call: the result is identical bit for bit
+    (tests/test_wavio.py)."""
+    global _DECODE_POOL
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    n = y.size
+    workers = min(8, os.cpu_count() or 1)
+    if n < 32768 or workers < 2:
+        return np.sign(y) / mu * ((1 + mu) ** np.abs(y) - 1)
+    if _DECODE_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _DECODE_POOL = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="wrnn-mulaw")
+    out = np.empty(n, dtype=np.float64)
+    step = -(-n // workers)
+    step = -(-step // 64) * 64
+
+    def part(a):
+        b = min(n, a + step)
+        out[a:b] = np.sign(y[a:b]) / mu * ((1 + mu) ** np.abs(y[a:b]) - 1)
+
+    list(_DECODE_POOL.map(part, range(0, n, step)))
+    return out
