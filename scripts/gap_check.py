@@ -1,5 +1,8 @@
+"""Development aid: step time of the wide kernel with random conditioning (what scripts/ab_time.py measures) against the same kernel
+inside generate() on BASELINE.json configs[1] and its ref-geometry twin.  Found the 1.6 us/step that the per-step zeroing of a padding
+fold's conditioning row cost (profiles/r02_summary.md section 4)."""
 import sys, os, numpy as np, torch
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from expressive_speech_synthesis_research_b200 import WaveRNN
 from oracle import synth
 dev = torch.device("cuda", 0)
