@@ -342,6 +342,12 @@ def test_wide_kernel_every_fold_count_and_ragged_limits(monkeypatch, mode):
     monkeypatch.setenv("WRNN_KERNEL", "wide")
     wid = run_folds(m, mels, aux, U, forced=forced, logits=True)
     assert np.abs(wid["logits"] - grp["logits"]).max() <= 2e-5
+    # very short runs (the conditioning prefetch, the end-of-step pass and the barrier phases have special cases at S = 1, 2, 3)
+    for S2 in (1, 2, 3):
+        monkeypatch.setenv("WRNN_KERNEL", "wide")
+        w = run_folds(m, mels[:, :S2], aux[:, :S2], np.ascontiguousarray(U[:S2]), forced=np.ascontiguousarray(forced[:S2]), logits=True)
+        assert np.array_equal(w["logits"], wid["logits"][:S2]), S2        # a prefix of the long run, bit for bit
+        assert np.array_equal(w["samples"], wid["samples"][:, :S2]), S2
     # ragged limits: fold f has only 5 + 2 f rows of conditioning, the rest of its steps read zeros
     dev = torch.device("cuda", 0)
     eng = m._engine(dev)
