@@ -367,6 +367,7 @@ def run_single(args, dev, local, barrier):
         device_step(i)
         e2e_step(i)
     info0 = eng.info()
+    cond0 = sum(c.launches() for c in model._conds.values())       # the frame-rate conditioning kernel (csrc/wavernn_cond.cuh)
     sampler = ClockSampler(local)
     sampler.start()
     # ---- kernel-resident leg -------------------------------------------------------------------
@@ -381,6 +382,7 @@ def run_single(args, dev, local, barrier):
     barrier()
     t_dev = ev0.elapsed_time(ev1) / 1e3
     info1 = eng.info()
+    cond1 = sum(c.launches() for c in model._conds.values())
     # ---- end-to-end leg (host buffers, H2D + D2H inside the timed region) ----------------------
     barrier()
     ev0.record()
@@ -419,7 +421,7 @@ def run_single(args, dev, local, barrier):
         "e2e": {"value": total_samples / t_e2e, "unit": "samples/s", "h2d_bytes_per_step": int(mel_host.numel() * 4),
                 "d2h_bytes_per_step": int(wl["wave_len"] * 8), "ms_per_step": t_e2e / args.steps * 1e3,
                 "rtf": (t_e2e / args.steps) / (wl["wave_len"] / wl["sr"])},
-        "gpu_launches": int((info1.launches - info0.launches) + (info1.epilogue_launches - info0.epilogue_launches)),
+        "gpu_launches": int((info1.launches - info0.launches) + (info1.epilogue_launches - info0.epilogue_launches) + (cond1 - cond0)),
         "clocks": clocks,
     }
     if kind == 1:

@@ -296,6 +296,19 @@ class WaveRNN(nn.Module):
     def conditioning(self, mels):
         """generate() prologue, fatchord_version.py:162-165: (1, feat, T) -> (L, feat), (L, 4*aux)."""
         m = F.pad(mels, (self.pad, self.pad))                       # pad_tensor(side='both'), :260-270
+        if mels.is_cuda and self.melresnet_native():
+            # aux = repeat(MelResNet(m), hop) with the CUDA kernel of csrc/wavernn_cond.cuh (one launch instead of ~65); the three
+            # (repeat, box filter) stages of the mel branch stay PyTorch convolutions in true fp32
+            T = int(mels.shape[-1])
+            af = torch.empty(T, 4 * self.aux_dims, dtype=torch.float32, device=mels.device)
+            self._cond(mels.device).frames(m[0].t().contiguous(), np.array([[0, T, 0]], dtype=np.int32), af)
+            aux = af.repeat_interleave(self.upsample.total_scale, dim=0)
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                mu = m.unsqueeze(1)
+                for layer in self.upsample.up_layers:
+                    mu = layer(mu)
+            mu = mu.squeeze(1)[:, :, self.upsample.indent:-self.upsample.indent]
+            return mu[0].t().contiguous(), aux
         m, aux = self.upsample_fp32(m)
         return m[0].contiguous(), aux[0].contiguous()
 
