@@ -966,9 +966,10 @@ static int32_t launch_wide(wrnn_handle *h, wrnn_wide::WParams &p, cudaStream_t s
     h->launches += 1;
     return WRNN_OK;
 }
-// Which fp32 kernel serves `num_folds` folds: the wide kernel's step (15 us) hardly depends on the fold count, the grouped
-// kernel's is 11.5 us for one group of <= 8 folds and 15.7 / 24 us for two / three (profiles/r02_summary.md): wide above 8.
-// WRNN_KERNEL=grouped | wide forces one (development knob).
+// Which fp32 kernel serves a call: the wide kernel whenever the model is one it is built for (fp32 RAW-512 / MOL).  Since its
+// publishes are whole 32-byte sectors it is at least as fast as the grouped kernel at every fold count (1 fold: 10.7 vs 11.2 us per
+// step, 8 folds: 11.07 vs 11.06, 20 folds: 12.0 vs 24.0; profiles/r02_summary.md).  The grouped kernel keeps bf16 resident weights and other
+// class counts.  wrnn_set_kernel / WRNN_KERNEL=grouped | wide force one (the two add partial sums in different orders).
 static bool use_wide(const wrnn_handle *h, int num_folds)
 {
     if (!h->wide) return false;
@@ -976,8 +977,8 @@ static bool use_wide(const wrnn_handle *h, int num_folds)
     if (h->kernel_choice == 1) return true;
     const char *k = getenv("WRNN_KERNEL");
     if (k && strcmp(k, "grouped") == 0) return false;
-    if (k && strcmp(k, "wide") == 0) return true;
-    return num_folds > BT;
+    (void)num_folds;
+    return true;
 }
 
 // dense step loop (csrc/wavernn_dense.cuh): one launch holds every fold; clusters are independent

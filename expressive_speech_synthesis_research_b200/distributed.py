@@ -165,8 +165,9 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                 B, _ = _lib.fold_index(L, target, overlap)
                 S = target + 2 * overlap
                 lo, hi = fold_ranges(B, world)[rank]
-                # the fp32 kernels differ in summation order: every rank runs the one the unsplit call would run (by ALL B folds)
-                eng.set_kernel(1 if B > 8 else 0)
+                # the fp32 kernels differ in summation order: every rank must run the one the unsplit call would run; that is the
+                # library's default for every fold count (the wide kernel where the model allows it), so nothing is pinned here
+                eng.set_kernel(-1)
                 if hi > lo:
                     starts = np.arange(lo, hi, dtype=np.int64) * (target + overlap)
                     u = None if uniforms is None else torch.as_tensor(uniforms)[:, lo:hi]

@@ -230,10 +230,10 @@ int32_t wrnn_get_stage_cycles(wrnn_handle *h, int64_t *out /* [host] */, int32_t
  * Writes the mean device time per exchange in microseconds.  Synchronous. */
 int32_t wrnn_measure_exchange(wrnn_handle *h, int32_t iters, float *usec_per_exchange);
 
-/* Which fp32 step-loop kernel serves the next calls on this handle: -1 (default) by the fold count of each call (the grouped kernel
- * up to 8 folds, the wide kernel above), 0 the grouped kernel, 1 the wide kernel.  The two kernels add their partial sums in different
- * orders, so a caller that splits one utterance's folds over several calls or GPUs (distributed.py::generate_sharded) pins the
- * kernel the unsplit call would use and gets the same samples bit for bit.  No effect on the dense precision. */
+/* Which fp32 step-loop kernel serves the next calls on this handle: -1 (default) the wide kernel whenever the model is one it is
+ * built for (fp32, RAW with 512 classes or MOL), else the grouped kernel; 0 the grouped kernel; 1 the wide kernel.  The two kernels add
+ * their partial sums in different orders, so their samples differ in the last bits: a caller comparing runs pins one.  No effect on
+ * the dense precision. */
 int32_t wrnn_set_kernel(wrnn_handle *h, int32_t choice);
 
 /* ---- frame-rate conditioning network (csrc/wavernn_cond.cuh) -------------------------------------------------------

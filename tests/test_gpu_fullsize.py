@@ -142,8 +142,10 @@ def test_progress_hook_and_auto_precision():
     m.precision = "auto"
     m.generate(synth.make_mel(60, seed=4), True, 700, 60, True, seed=2)                  # 16 folds
     assert m.last_stats["kernel_kind"] == 1
-    m.generate(synth.make_mel(25, seed=4), True, 700, 60, True, seed=2)                  # 7 folds: one group of the round-1 kernel is faster
-    assert m.last_stats["kernel_kind"] == 0
+    m.generate(synth.make_mel(25, seed=4), True, 700, 60, True, seed=2)                  # 7 folds: the wide kernel at every fold count
+    assert m.last_stats["kernel_kind"] == 1
+    m.generate(synth.make_mel(25, seed=4), False, 700, 60, True, seed=2)                 # unbatched: one fold of 4 800 steps
+    assert m.last_stats["kernel_kind"] == 1
     m.generate_many([synth.make_mel(60, seed=50 + i) for i in range(12)], 700, 60, True, seed=3)   # 12 x 16 folds > 64
     assert m.last_stats["kernel_kind"] == 2
     m.precision = "fp32"

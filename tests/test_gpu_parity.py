@@ -315,7 +315,7 @@ def test_results_do_not_depend_on_the_team_layout(monkeypatch):
 
 @pytest.mark.parametrize("mode", ["RAW", "MOL"])
 def test_wide_kernel_every_fold_count_and_ragged_limits(monkeypatch, mode):
-    """The wide kernel (csrc/wavernn_wide.cuh) forced for EVERY fold count 1..21 (the dispatcher only sends it more than 8): nq = 1..7
+    """The wide kernel (csrc/wavernn_wide.cuh) at EVERY fold count 1..21: nq = 1..7
     quads per unit, sampler warps with and without a fold, finalize threads without a quad.  A fold's samples and logits must not
     depend on how many folds share its launch (the partial sums are added in a fixed order and handed between the pass warps and
     the finalize warps through named barriers + a consumption counter: a lost hand-off shows up here), must match the grouped
