@@ -14,13 +14,15 @@ so the path shards without any collective inside the step loop (SURVEY.md sectio
   single-GPU waveform because every output sample is still (0 + a*fade_out) + b*fade_in in fp64.
 """
 import ctypes
+import os
+import time
 
 import numpy as np
 import torch
 import torch.distributed as dist
 
 from . import _lib
-from .wavio import decode_mu_law_host
+from .wavio import decode_mu_law_host, parallel_copy
 
 
 def plan_utterances(fold_counts, world_size):
@@ -127,10 +129,17 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     mu_law = mu_law if model.mode == 'RAW' else False
     model.eval()
+    trace = [] if os.environ.get("WRNN_TRACE") else None      # development: host timeline of the call (device synchronised at every mark)
+
+    def mark(what):
+        if trace is not None:
+            torch.cuda.synchronize()
+            trace.append((what, time.perf_counter()))
     try:
         with torch.no_grad():
             device = model._device()
             with torch.cuda.device(device):
+                mark("start")
                 eng = model._engine(device)
                 nfolds_total, _ = _lib.fold_index(mels.size(-1) * model.hop_length, target, overlap)
                 eng = model._pick_engine(eng, device, -(-nfolds_total // world))      # regime by the folds of ONE rank
@@ -162,6 +171,7 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                 else:
                     m_up, aux = model.conditioning(mels)
                     L = m_up.size(0)
+                mark("conditioning")
                 B, _ = _lib.fold_index(L, target, overlap)
                 S = target + 2 * overlap
                 lo, hi = fold_ranges(B, world)[rank]
@@ -189,11 +199,13 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                     model._pinned("sharded", wave_len)
                 if hi > lo:
                     eng.synchronize()                                             # watchdog status of the step loop
+                mark("step loop (+ output array prepared)")
                 # same decode policy as WaveRNN.generate: bit-exact numpy mu-law + tail fade on the host below 2 M samples
                 host_mu = bool(mu_law) and gather_to is not None and (
                     model.mu_law_decode == "host" or (model.mu_law_decode == "auto" and wave_len < 2_000_000))
                 wav = finish_sharded(local, lo, hi, B, target, overlap, model.n_classes if (mu_law and not host_mu) else 0, wave_len,
                                      0 if host_mu else 20 * model.hop_length, group=group, gather_to=gather_to)
+                mark("edges, epilogue, gather to root")
                 if wav is None:
                     return None
                 host = model._pinned("sharded", wav.numel())            # pinned landing buffer: 106 MB of a 10-minute utterance at PCIe speed
@@ -201,8 +213,12 @@ def generate_sharded(model, mels, target, overlap, mu_law, uniforms=None, seed=0
                 torch.cuda.current_stream(device).synchronize()
                 if out is None or out.size != wav.numel():
                     out = np.empty(wav.numel(), dtype=np.float64)
-                torch.from_numpy(out).copy_(host)                       # multi-threaded copy into the pre-faulted array
+                mark("D2H")
+                parallel_copy(out, host.numpy())                        # a few threads, into the pre-faulted array
                 wav = out
+                mark("copy to the caller's array")
+                if trace is not None:
+                    print("generate_sharded timeline (ms): " + ", ".join("%s +%.1f" % (w, (t - trace[i][1]) * 1e3) for i, (w, t) in enumerate(trace[1:])), flush=True)
                 if host_mu:
                     mu = model.n_classes - 1
                     wav = decode_mu_law_host(wav, mu)             # decode_mu_law, dsp.py:100-105

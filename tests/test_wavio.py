@@ -52,3 +52,12 @@ def test_threaded_mu_law_decode_is_bit_identical_to_the_reference_expression():
     np.sign(y) / mu * ((1 + mu) ** np.abs(y) - 1)
     t2 = time.perf_counter()
     print("mu-law decode of 220550 samples: %.2f ms threaded, %.2f ms one call" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+
+
+def test_parallel_copy_copies_everything():
+    from expressive_speech_synthesis_research_b200.wavio import parallel_copy
+    rng = np.random.default_rng(1)
+    for n in (0, 5, (1 << 20) - 1, (1 << 20) + 3, 3_000_001):
+        src = rng.standard_normal(n)
+        dst = np.full(n, np.nan)
+        assert parallel_copy(dst, src) is dst and np.array_equal(dst, src)
