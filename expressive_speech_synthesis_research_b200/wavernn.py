@@ -836,11 +836,11 @@ class WaveRNN(nn.Module):
                         flat, w0 = job["wav_host"].numpy(), 0
                         for i in job["chunk"]:
                             wave_len = plan[i][2]
-                            wav = flat[w0:w0 + wave_len].copy()
-                            if host_mu:
-                                mu = self.n_classes - 1
-                                wav = decode_mu_law_host(wav, mu)
+                            if host_mu:                                  # the decode writes a fresh array: no copy out of the pinned buffer first
+                                wav = decode_mu_law_host(flat[w0:w0 + wave_len], self.n_classes - 1)
                                 wav[-20 * self.hop_length:] *= np.linspace(1, 0, 20 * self.hop_length)
+                            else:
+                                wav = flat[w0:w0 + wave_len].copy()
                             outs[i] = wav
                             if writer is not None:
                                 writer(i, wav)
